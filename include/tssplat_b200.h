@@ -1,0 +1,107 @@
+/* tssplat_b200 -- C ABI of the B200-native geometry-energy hot path of TetSphere Splatting.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference checkout,
+ * gmh14/tssplat @ 0241e9e3).  The reference-side binding a maintainer would add is shown in
+ * INTEGRATION.md; the in-repo Python binding is tssplat_b200/_capi.py (ctypes).
+ *
+ * All device pointers are CUDA device pointers on the handle's device.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns 0 on
+ * success and a negative TSB_E_* code on failure; tsb_last_error() gives the message.
+ * A handle is not re-entrant (it owns scratch buffers), exactly like the reference's TetSpheres
+ * object (tssplat_ext/tet_spheres/tet_spheres.h:37).
+ */
+#ifndef TSSPLAT_B200_H_
+#define TSSPLAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSB_VERSION 1
+
+enum {
+  TSB_OK = 0,
+  TSB_E_INVALID = -1,   /* bad argument (null pointer, order not in {2,4}, sizes <= 0, ...)      */
+  TSB_E_MESH = -2,      /* bad mesh: index out of range, zero-volume rest tet, non-manifold face */
+  TSB_E_CUDA = -3,      /* a CUDA runtime call failed                                            */
+  TSB_E_NOMEM = -4
+};
+
+typedef struct tsb_handle_s *tsb_handle_t;
+
+typedef struct {
+  int32_t tile_tets;        /* tets per tile (CTA work unit); 0 = library default               */
+  int32_t laplacian_scale;  /* 0 = unscaled tet-graph Laplacian (what the reference requests:
+                               tet_spheres.cpp:148 passes (1, 0)); 1 = rows divided by #nbrs    */
+  int32_t reserved[6];
+} tsb_options_t;
+
+typedef struct {
+  int32_t n;                /* vertices                                                          */
+  int32_t nele;             /* tets                                                              */
+  int32_t n_tiles;          /* CTAs per launch                                                   */
+  int32_t tile_tets;
+  int32_t n_components;     /* connected components (= tet-spheres)                              */
+  int32_t n_shared_vertices;/* vertices touched by more than one tile                            */
+  int64_t n_local_vertices; /* sum over tiles of staged vertices (duplication = this / n)        */
+  int64_t device_bytes;     /* bytes of device memory owned by the handle                        */
+  int64_t stream_bytes;     /* bytes one launch reads+writes from the handle's arrays + x + grad */
+  int32_t n_boundary_faces;
+  int32_t max_local_vertices;
+} tsb_info_t;
+
+/* Replaces TetSpheres::TetSpheres(int nv, double*, int ntet, int*) + TetSpheres::init
+ * (tssplat_ext/tet_spheres/tet_spheres.cpp:119-126,140-203) and the libpgo operator builders it
+ * calls (:148-149): builds per-tet rest inverses, face adjacency and the tile plan on the host,
+ * uploads them to `device`.  rest_xyz: host float32 [3n] REST positions; tets: host int32
+ * [4*nele], 0-based.  opt may be NULL. */
+int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele,
+               const tsb_options_t *opt, int device, tsb_handle_t *out);
+
+/* Replaces TetSpheres::~TetSpheres (tet_spheres.cpp:128-138); frees everything (no leaks). */
+void tsb_destroy(tsb_handle_t h);
+
+/* Message of the last failure on this handle (h may be NULL: last tsb_create failure). */
+const char *tsb_last_error(tsb_handle_t h);
+
+int tsb_get_info(tsb_handle_t h, tsb_info_t *info);
+
+/* THE HOT PATH.  Replaces tet_spheres_smooth_barrier + tet_spheres_smooth_barrier_backward
+ * (tssplat_ext/tet_spheres/tet_spheres_cuda.cu:118-195 and :197-263: 5 cuSPARSE SpMVs, 2 kernels,
+ * 3 cuBLAS calls and 3 host syncs) with ONE kernel launch and no host sync:
+ *   energy_out[0] = c1 * 1/2 ||L G x||^2 + c2 * sum_t max(-det F_t,0)^order
+ *   energy_out[1] = 1/2 ||L G x||^2          energy_out[2] = sum_t max(-det F_t,0)^order
+ *   grad_out      = gradH * d energy_out[0] / d x          ([n,3] fp32, fully overwritten)
+ * x_dev: device float32 [3n], contiguous.  gradH_dev: optional device float (0-dim tensor's
+ * data pointer); when non-NULL it multiplies gradH (so pass gradH = 1).  grad_out_dev may be NULL
+ * (energy only: replaces the forward alone).  order must be 2 or 4 (the reference silently
+ * returns zeros otherwise: cu:57-63). */
+int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order,
+                    float gradH, const float *gradH_dev, float *energy_out_dev,
+                    float *grad_out_dev, void *stream);
+
+/* out = gradH * (*gradH_dev) * g  -- the cublasSscal at tet_spheres_cuda.cu:257-258 without the
+ * .item() sync.  In-place allowed. */
+int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH_dev,
+              float *out_dev, void *stream);
+
+/* Replaces tet_spheres_grad_limit (tet_spheres_cuda.cu:265-303) with what it was meant to do
+ * (the reference reads grad[0] instead of the arg-max element and is unused by the trainer):
+ * if max|grad| > s_threshold, grad *= s / max|grad|.  No host sync. */
+int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, void *stream);
+
+/* "Next" row (f)1: AdamUniform.step (utils/optimizer.py:37-89) as two launches and no sync.
+ * p, g1, g2: device float32 [count]; step is the 1-based step number AFTER increment.
+ * grad_limit <= 0 disables the clamp (optimizer.py:76-86).  work_dev: device float32 [4]
+ * scratch owned by the caller (zero-initialised once; the kernels leave it zeroed). */
+int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, float *g2_dev,
+                          int64_t count, float lr, float beta1, float beta2, int32_t step,
+                          float grad_limit, float *work_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSSPLAT_B200_H_ */

@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI declared in ``include/tssplat_b200.h``.
+
+There is no CPU fallback: if ``libtssplat_b200.so`` is missing or does not load, importing the
+product modules raises.  Build it with ``python -m tssplat_b200.build`` (needs nvcc, no GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+LIB_PATH = _build.LIB_PATH
+
+TSB_OK, TSB_E_INVALID, TSB_E_MESH, TSB_E_CUDA, TSB_E_NOMEM = 0, -1, -2, -3, -4
+
+# every symbol include/tssplat_b200.h declares (tests check the library exports each one)
+EXPORTED_SYMBOLS = (
+    "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_scale",
+    "tsb_grad_limit", "tsb_adam_uniform_step",
+)
+
+
+class tsb_options_t(C.Structure):
+    _fields_ = [("tile_tets", C.c_int32), ("laplacian_scale", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class tsb_info_t(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("nele", C.c_int32), ("n_tiles", C.c_int32), ("tile_tets", C.c_int32),
+        ("n_components", C.c_int32), ("n_shared_vertices", C.c_int32),
+        ("n_local_vertices", C.c_int64), ("device_bytes", C.c_int64), ("stream_bytes", C.c_int64),
+        ("n_boundary_faces", C.c_int32), ("max_local_vertices", C.c_int32),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the B200 CUDA library has not been built "
+            "(run `python -m tssplat_b200.build`); tssplat_b200 has no CPU fallback")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise ImportError(f"cannot load {LIB_PATH}: {e}; tssplat_b200 has no CPU fallback") from e
+    vp, f32, i32, i64 = C.c_void_p, C.c_float, C.c_int32, C.c_int64
+    lib.tsb_create.restype = C.c_int
+    lib.tsb_create.argtypes = [vp, vp, i32, i32, C.POINTER(tsb_options_t), C.c_int, C.POINTER(vp)]
+    lib.tsb_destroy.restype = None
+    lib.tsb_destroy.argtypes = [vp]
+    lib.tsb_last_error.restype = C.c_char_p
+    lib.tsb_last_error.argtypes = [vp]
+    lib.tsb_get_info.restype = C.c_int
+    lib.tsb_get_info.argtypes = [vp, C.POINTER(tsb_info_t)]
+    lib.tsb_energy_grad.restype = C.c_int
+    lib.tsb_energy_grad.argtypes = [vp, vp, f32, f32, i32, f32, vp, vp, vp, vp]
+    lib.tsb_scale.restype = C.c_int
+    lib.tsb_scale.argtypes = [vp, i64, f32, vp, vp, vp]
+    lib.tsb_grad_limit.restype = C.c_int
+    lib.tsb_grad_limit.argtypes = [vp, i64, f32, f32, vp]
+    lib.tsb_adam_uniform_step.restype = C.c_int
+    lib.tsb_adam_uniform_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, i32, f32, vp, vp]
+    return lib
+
+
+lib = _load()
+
+
+def last_error(handle=None) -> str:
+    msg = lib.tsb_last_error(handle)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, handle=None, what: str = "tssplat_b200") -> None:
+    """Non-zero return codes become exceptions, like the reference's throw std::runtime_error
+    (``tssplat_ext/tet_spheres/tet_spheres.cpp:152-202``)."""
+    if rc == TSB_OK:
+        return
+    raise RuntimeError(f"{what}: {last_error(handle)} (code {rc})")

@@ -1,0 +1,266 @@
+// C ABI (include/tssplat_b200.h) over the plan builder and the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tssplat_b200.h"
+#include "tsb_kernels.cuh"
+#include "tsb_plan.h"
+
+struct tsb_handle_s {
+  int device = 0;
+  tsb::KParams kp{};
+  tsb_info_t info{};
+  std::vector<void *> allocs;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+std::mutex g_mu;
+std::map<int, float *> g_limit_work;  // per-device scratch for tsb_grad_limit
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(tsb_handle_t h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+template <class T>
+int upload(tsb_handle_t h, const std::vector<T> &v, const T **out, size_t min_elems = 1) {
+  const size_t bytes = std::max(v.size(), min_elems) * sizeof(T);
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) return fail(h, TSB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(d);
+  h->info.device_bytes += int64_t(bytes);
+  if (!v.empty()) {
+    e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+  }
+  *out = static_cast<const T *>(d);
+  return TSB_OK;
+}
+
+template <class T>
+int alloc_zero(tsb_handle_t h, size_t elems, T **out) {
+  const size_t bytes = std::max<size_t>(elems, 1) * sizeof(T);
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) return fail(h, TSB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(d);
+  h->info.device_bytes += int64_t(bytes);
+  e = cudaMemset(d, 0, bytes);
+  if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  *out = static_cast<T *>(d);
+  return TSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele, const tsb_options_t *opt,
+               int device, tsb_handle_t *out) {
+  if (!out) return fail(nullptr, TSB_E_INVALID, "out is null");
+  *out = nullptr;
+  tsb::PlanOptions po;
+  if (opt) {
+    if (opt->tile_tets != 0) po.tile_tets = opt->tile_tets;
+    po.laplacian_scale = opt->laplacian_scale ? 1 : 0;
+  }
+  if (const char *env = std::getenv("TSSPLAT_B200_TILE_TETS")) {
+    if (!(opt && opt->tile_tets != 0)) po.tile_tets = std::atoi(env);
+  }
+  po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
+  if (po.max_local_vertices == 0)
+    return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets " + std::to_string(po.tile_tets) + " (compiled: 256, 512, 1024)");
+
+  tsb::HostPlan plan;
+  std::string err;
+  int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, plan, err);
+  if (rc != TSB_OK) return fail(nullptr, rc, err);
+
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(nullptr, TSB_E_CUDA, "cannot select CUDA device " + std::to_string(device));
+  cudaError_t ce = tsb::prepare_energy_grad(po.tile_tets, po.max_local_vertices);
+  if (ce != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(ce));
+
+  tsb_handle_t h = new tsb_handle_s();
+  h->device = device;
+  tsb::KParams &kp = h->kp;
+  const uint16_t *idx16 = nullptr;
+#define TSB_TRY(expr) do { rc = (expr); if (rc != TSB_OK) { g_create_err = h->err; tsb_destroy(h); return rc; } } while (0)
+  TSB_TRY(upload(h, plan.tiles, &kp.tiles));
+  TSB_TRY(upload(h, plan.idx8, &idx16, 8));
+  kp.idx8 = reinterpret_cast<const uint4 *>(idx16);
+  TSB_TRY(upload(h, plan.Bsoa, &kp.Bsoa));
+  TSB_TRY(upload(h, plan.vlist, &kp.vlist));
+  TSB_TRY(upload(h, plan.Xloc, &kp.Xloc));
+  TSB_TRY(upload(h, plan.dest, &kp.dest));
+  TSB_TRY(upload(h, plan.ell, &kp.ell));
+  TSB_TRY(upload(h, plan.ell_grp_ptr, &kp.ell_grp_ptr));
+  TSB_TRY(upload(h, plan.cg_list, &kp.cg_list));
+  TSB_TRY(upload(h, plan.need, &kp.need));
+  TSB_TRY(upload(h, plan.gsv_ptr, &kp.gsv_ptr));
+  TSB_TRY(upload(h, plan.sv_vid, &kp.sv_vid));
+  TSB_TRY(upload(h, plan.sv_slot_ptr, &kp.sv_slot_ptr));
+  TSB_TRY(alloc_zero(h, size_t(plan.n_tiles), &kp.done));
+  TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 3, &kp.scratch));
+  TSB_TRY(alloc_zero(h, size_t(plan.n_tiles) * 2, &kp.tile_energy));
+  TSB_TRY(alloc_zero(h, 1, &kp.energy_counter));
+#undef TSB_TRY
+  kp.laplacian_scale = plan.laplacian_scale;
+  kp.n_tiles = plan.n_tiles;
+
+  tsb_info_t &I = h->info;
+  I.n = plan.n; I.nele = plan.nele; I.n_tiles = plan.n_tiles; I.tile_tets = plan.tile_tets;
+  I.n_components = plan.n_components; I.n_shared_vertices = plan.n_shared_vertices;
+  I.n_local_vertices = plan.n_local_vertices; I.n_boundary_faces = plan.n_boundary_faces;
+  I.max_local_vertices = plan.max_local_vertices;
+  // bytes one launch moves through the memory system (useful tile payload, not padding):
+  //   per tet 16 (stencil ids) + 36 (rest inverse); per staged vertex 4 (id) + 12 (x) + 12 (X) + 4 (dest);
+  //   gather table 2 B/entry; grad 12 B/vertex; shared-vertex partials written + read
+  I.stream_bytes = int64_t(plan.nele) * 52 + plan.n_local_vertices * 32 + int64_t(plan.ell.size()) * 2 +
+                   int64_t(plan.n) * 12 + int64_t(plan.n_slots) * 24 + int64_t(plan.n_tiles) * (32 + 8);
+  *out = h;
+  return TSB_OK;
+}
+
+void tsb_destroy(tsb_handle_t h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  for (void *p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+const char *tsb_last_error(tsb_handle_t h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int tsb_get_info(tsb_handle_t h, tsb_info_t *info) {
+  if (!h || !info) return TSB_E_INVALID;
+  *info = h->info;
+  return TSB_OK;
+}
+
+int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order, float gradH,
+                    const float *gradH_dev, float *energy_out_dev, float *grad_out_dev, void *stream) {
+  if (!h) return TSB_E_INVALID;
+  if (!x_dev || !energy_out_dev) return fail(h, TSB_E_INVALID, "x_dev and energy_out_dev must be non-null");
+  if (order != 2 && order != 4)
+    return fail(h, TSB_E_INVALID, "order must be 2 or 4 (the reference yields zeros for anything else: tet_spheres_cuda.cu:57-63)");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, TSB_E_CUDA, "cannot select the handle's CUDA device");
+  tsb::KParams kp = h->kp;
+  kp.x = x_dev; kp.grad = grad_out_dev; kp.energy_out = energy_out_dev; kp.gradH_dev = gradH_dev;
+  kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
+  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, h->info.max_local_vertices, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
+  return TSB_OK;
+}
+
+int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH_dev, float *out_dev, void *stream) {
+  if (!g_dev || !out_dev || count < 0) return fail(nullptr, TSB_E_INVALID, "tsb_scale: null pointer or negative count");
+  if (count == 0) return TSB_OK;
+  cudaError_t e = tsb::launch_scale(g_dev, count, gradH, gradH_dev, out_dev, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("scale launch: ") + cudaGetErrorString(e));
+  return TSB_OK;
+}
+
+int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, void *stream) {
+  if (!grad_dev || count < 0) return fail(nullptr, TSB_E_INVALID, "tsb_grad_limit: null pointer or negative count");
+  if (count == 0) return TSB_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, TSB_E_CUDA, "cudaGetDevice failed");
+  float *work = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_limit_work.find(dev);
+    if (it == g_limit_work.end()) {
+      if (cudaMalloc(reinterpret_cast<void **>(&work), 4 * sizeof(float)) != cudaSuccess || cudaMemset(work, 0, 4 * sizeof(float)) != cudaSuccess)
+        return fail(nullptr, TSB_E_NOMEM, "tsb_grad_limit: scratch allocation failed");
+      g_limit_work[dev] = work;
+    } else {
+      work = it->second;
+    }
+  }
+  cudaError_t e = tsb::launch_grad_limit(grad_dev, count, s_threshold, s, work, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("grad_limit launch: ") + cudaGetErrorString(e));
+  return TSB_OK;
+}
+
+int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, float *g2_dev, int64_t count, float lr,
+                          float beta1, float beta2, int32_t step, float grad_limit, float *work_dev, void *stream) {
+  if (!p_dev || !grad_dev || !g1_dev || !g2_dev || !work_dev || count < 0 || step < 1)
+    return fail(nullptr, TSB_E_INVALID, "tsb_adam_uniform_step: null pointer, negative count or step < 1");
+  if (count == 0) return TSB_OK;
+  cudaError_t e = tsb::launch_adam_uniform(p_dev, grad_dev, g1_dev, g2_dev, count, lr, beta1, beta2, step, grad_limit,
+                                           work_dev, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("adam_uniform launch: ") + cudaGetErrorString(e));
+  return TSB_OK;
+}
+
+/* ---- host-plan inspection (tests only; no CUDA calls): lets the CPU test-suite check the tile
+ * plan -- staging lists, gather tables, shared-vertex combine lists -- without a GPU. ---------- */
+struct tsb_debug_plan_s { tsb::HostPlan plan; };
+
+int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele, int32_t tile_tets,
+                         int32_t laplacian_scale, tsb_debug_plan_s **out) {
+  if (!out) return TSB_E_INVALID;
+  *out = nullptr;
+  tsb::PlanOptions po;
+  if (tile_tets) po.tile_tets = tile_tets;
+  po.laplacian_scale = laplacian_scale;
+  po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
+  if (po.max_local_vertices == 0) return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets");
+  tsb_debug_plan_s *d = new tsb_debug_plan_s();
+  std::string err;
+  const int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, d->plan, err);
+  if (rc != TSB_OK) { delete d; return fail(nullptr, rc, err); }
+  *out = d;
+  return TSB_OK;
+}
+
+/* name -> (pointer, element count, element bytes); returns TSB_E_INVALID for an unknown name */
+int tsb_debug_plan_array(tsb_debug_plan_s *d, const char *name, const void **ptr, int64_t *count, int32_t *elem_bytes) {
+  if (!d || !name || !ptr || !count || !elem_bytes) return TSB_E_INVALID;
+  const tsb::HostPlan &P = d->plan;
+  const std::string k(name);
+#define TSB_ARR(nm, vec) if (k == nm) { *ptr = (vec).data(); *count = int64_t((vec).size()); *elem_bytes = int32_t(sizeof((vec)[0])); return TSB_OK; }
+  TSB_ARR("tiles", P.tiles) TSB_ARR("idx8", P.idx8) TSB_ARR("Bsoa", P.Bsoa) TSB_ARR("vlist", P.vlist)
+  TSB_ARR("Xloc", P.Xloc) TSB_ARR("dest", P.dest) TSB_ARR("ell", P.ell) TSB_ARR("ell_grp_ptr", P.ell_grp_ptr)
+  TSB_ARR("cg_list", P.cg_list) TSB_ARR("need", P.need) TSB_ARR("gsv_ptr", P.gsv_ptr) TSB_ARR("sv_vid", P.sv_vid)
+  TSB_ARR("sv_slot_ptr", P.sv_slot_ptr) TSB_ARR("tet_order", P.tet_order)
+#undef TSB_ARR
+  return TSB_E_INVALID;
+}
+
+int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {
+  if (!d || !out8) return TSB_E_INVALID;
+  const tsb::HostPlan &P = d->plan;
+  out8[0] = P.n; out8[1] = P.nele; out8[2] = P.tile_tets; out8[3] = P.max_local_vertices; out8[4] = P.n_tiles;
+  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots;
+  return TSB_OK;
+}
+
+void tsb_debug_plan_free(tsb_debug_plan_s *d) { delete d; }
+
+/* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
+void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
+
+}  // extern "C"

@@ -1,0 +1,477 @@
+// Fused geometry-energy + gradient kernel for sm_100a, plus the small level-1 helpers.
+//
+// One launch replaces the reference's forward+backward pipeline
+// (tssplat_ext/tet_spheres/tet_spheres_cuda.cu:118-263: SpMV GTLTLG.x, Sdot, SpMV G.x,
+// cuda_forward_det, Sasum, SpMV c1.GTLTLG.x, SpMV G.x again, cuda_backward_det, SpMV G^T, Sscal,
+// with three host syncs).
+//
+// Math.  For tet t with own vertices v0..v3, rest inverse B = Dm^-1 (rows
+// a1,a2,a3 are the rest gradients of the hat functions of v1..v3, a0 = -(a1+a2+a3)):
+//     F_t = sum_k x_vk (x) a_k                                (geometry/mesh_utils.py:38-69)
+// The reference's smoothness term 1/2 x^T G^T L^T L G x equals 1/2 sum_t ||H_t||^2 with
+// H_t = (L F)_t = deg_t F_t - sum_{s face-nbr t} F_s.  Two tets sharing a face agree on that face,
+// so F_s - F_t is rank one:  F_s - F_t = d_k (x) a_k / lambda_kk  where o_k is the vertex of s
+// opposite the shared face k, lambda_k. are the barycentric coordinates of REST(o_k) in t and
+//     d_k = x_ok - sum_j lambda_kj x_vj          (how far o_k is from t's affine map)
+// Hence  H_t = sum_k rho_k d_k (x) a_k,  rho_k = -1/lambda_kk > 0:  an 8-vertex stencil per tet
+// whose gradient scatters to those same 8 vertices -- no neighbour-tet intermediates, no 2-ring
+// passes, no grid sync.  The barrier term is the reference's: max(-det F,0)^p, p in {2,4}
+// (cu:48-66), gradient -p(-J)^(p-1) cof(F) (cu:68-102).
+//
+// Execution.  One CTA per tile (<= TT tets, <= NVMAX staged vertices):
+//   phase 0  stage x (gathered through vlist) and rest X of the tile's vertices in shared memory
+//   phase 1  one tet per thread: gather 8 vertices from smem, energy terms, 8 output 3-vectors
+//            written to a [24][TT] smem table (conflict-free stores)
+//   phase 2  one staged vertex per thread: sum its table entries through a 32-wide sliced-ELL
+//            list (coalesced u16 loads, deterministic order); vertices touched by this tile only
+//            are stored straight to grad, shared ones go to a per-(tile,vertex) scratch slot
+//   phase 3  last-arriver combine: per owner tile an arrival counter; the CTA that completes a
+//            group sums its shared vertices' slots in fixed order -> deterministic, single launch.
+//            Same pattern folds the per-tile energies (fp64, fixed order) into energy_out.
+// No global atomics on data, only on the arrival counters.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+
+#include "tsb_kernels.cuh"
+
+namespace tsb {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int TT, int NVMAX>
+struct Smem {
+  static constexpr int kXs4Bytes = NVMAX * 16;
+  static constexpr int kXs2Bytes = NVMAX * 8;
+  static constexpr int kOutBytes = 24 * TT * 4;
+  static constexpr int kBytes = kXs4Bytes + kXs2Bytes + kOutBytes;
+};
+
+template <int TT, int NVMAX, int NT, bool WITH_GRAD>
+__global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *xs4 = reinterpret_cast<float4 *>(smem_raw);                                  // x, y, z, X
+  float2 *xs2 = reinterpret_cast<float2 *>(smem_raw + Smem<TT, NVMAX>::kXs4Bytes);     // Y, Z
+  float *outb = reinterpret_cast<float *>(smem_raw + Smem<TT, NVMAX>::kXs4Bytes + Smem<TT, NVMAX>::kXs2Bytes);
+  __shared__ float s_red[2 * (NT / 32)];
+  __shared__ int s_flag[33];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const TileDesc td = p.tiles[tile];
+
+  // ---------------- phase 0: stage vertices ---------------------------------------------------
+  for (int i = tid; i < td.nvert; i += NT) {
+    const int g = __ldg(p.vlist + td.vert_off + i);
+    const float *xp = p.x + 3 * size_t(g);
+    const float *Xp = p.Xloc + 3 * size_t(td.vert_off + i);
+    const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+    const float X0 = __ldg(Xp), X1 = __ldg(Xp + 1), X2 = __ldg(Xp + 2);
+    xs4[i] = make_float4(x0, x1, x2, X0);
+    xs2[i] = make_float2(X1, X2);
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: tets -----------------------------------------------------------------
+  float es = 0.f, eb = 0.f;
+  const float c1 = p.c1, c2 = p.c2;
+  const int order = p.order;
+  for (int lt = tid; lt < td.ntet; lt += NT) {
+    const uint4 iv = __ldg(p.idx8 + size_t(tile) * TT + lt);
+    const float *Bp = p.Bsoa + size_t(tile) * 9 * TT + lt;
+    float b[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) b[i] = __ldg(Bp + i * TT);
+    const unsigned iown[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
+    const unsigned iopp[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
+
+    const float4 p0 = xs4[iown[0]];
+    const float2 q0 = xs2[iown[0]];
+    float e[3][3];  // e[j][r] = x_{v_{j+1}}[r] - x_{v0}[r]
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 pj = xs4[iown[j + 1]];
+      e[j][0] = pj.x - p0.x; e[j][1] = pj.y - p0.y; e[j][2] = pj.z - p0.z;
+    }
+    // hat gradients: a[0] = -(a1+a2+a3), a[j] = row j-1 of B
+    float a[4][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a[1][c] = b[c]; a[2][c] = b[3 + c]; a[3][c] = b[6 + c];
+      a[0][c] = -(b[c] + b[3 + c] + b[6 + c]);
+    }
+
+    float z[4][3];  // gradient contributions to own vertices
+    {
+      float F[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) F[r][c] = e[0][r] * a[1][c] + e[1][r] * a[2][c] + e[2][r] * a[3][c];
+      // cofactors = d det / dF  (tet_spheres_cuda.cu:32-46)
+      float C[3][3];
+      C[0][0] = F[1][1] * F[2][2] - F[1][2] * F[2][1];
+      C[0][1] = F[1][2] * F[2][0] - F[1][0] * F[2][2];
+      C[0][2] = F[1][0] * F[2][1] - F[1][1] * F[2][0];
+      const float J = F[0][0] * C[0][0] + F[0][1] * C[0][1] + F[0][2] * C[0][2];
+      if (J < 0.f) {
+        const float m = -J;
+        float coef;
+        if (order == 2) { eb += m * m; coef = 2.f * m; }
+        else { const float m2 = m * m; eb += m2 * m2; coef = 4.f * m2 * m; }
+        if (WITH_GRAD) {
+          C[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
+          C[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0];
+          C[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
+          C[2][0] = F[0][1] * F[1][2] - F[0][2] * F[1][1];
+          C[2][1] = F[0][2] * F[1][0] - F[0][0] * F[1][2];
+          C[2][2] = F[0][0] * F[1][1] - F[0][1] * F[1][0];
+          const float pc = -c2 * coef;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float P0 = pc * C[r][0], P1 = pc * C[r][1], P2 = pc * C[r][2];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) z[j][r] = P0 * a[j][0] + P1 * a[j][1] + P2 * a[j][2];
+            z[0][r] = -(z[1][r] + z[2][r] + z[3][r]);
+          }
+        }
+      } else if (WITH_GRAD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
+      }
+    }
+
+    // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k
+    float H[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { H[r][0] = 0.f; H[r][1] = 0.f; H[r][2] = 0.f; }
+    float lam[4][3], rho[4];
+    int deg = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rho[k] = 0.f; lam[k][0] = 0.f; lam[k][1] = 0.f; lam[k][2] = 0.f;
+      if (iopp[k] != 0xffffu) {
+        ++deg;
+        const float4 po = xs4[iopp[k]];
+        const float2 qo = xs2[iopp[k]];
+        const float rx = po.w - p0.w, ry = qo.x - q0.x, rz = qo.y - q0.y;
+        const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
+        const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
+        const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
+        const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
+        const float rk = -1.f / lkk;
+        lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float xo = (r == 0) ? po.x : (r == 1 ? po.y : po.z);
+          const float x0 = (r == 0) ? p0.x : (r == 1 ? p0.y : p0.z);
+          const float d = (xo - x0) - l1 * e[0][r] - l2 * e[1][r] - l3 * e[2][r];
+          const float s = rk * d;
+          H[r][0] += s * a[k][0]; H[r][1] += s * a[k][1]; H[r][2] += s * a[k][2];
+        }
+      }
+    }
+    const float w = (p.laplacian_scale && deg > 0) ? 1.f / float(deg) : 1.f;
+    float hh = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { H[r][c] *= w; hh += H[r][c] * H[r][c]; }
+    es += 0.5f * hh;
+
+    if (WITH_GRAD) {
+      const float cw = c1 * w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (iopp[k] != 0xffffu) {
+          const float sk = cw * rho[k];
+          const float l0 = 1.f - lam[k][0] - lam[k][1] - lam[k][2];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
+            outb[((4 + k) * 3 + r) * TT + lt] = y;
+            z[0][r] -= l0 * y; z[1][r] -= lam[k][0] * y; z[2][r] -= lam[k][1] * y; z[3][r] -= lam[k][2] * y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) outb[(j * 3 + r) * TT + lt] = z[j][r];
+    }
+  }
+
+  // per-tile energy partials (tree reduction; the cross-tile sum is done in fp64 below)
+  {
+    const float ws = warp_sum(es), wb = warp_sum(eb);
+    if ((tid & 31) == 0) { s_red[tid >> 5] = ws; s_red[NT / 32 + (tid >> 5)] = wb; }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float vs = (tid < NT / 32) ? s_red[tid] : 0.f, vb = (tid < NT / 32) ? s_red[NT / 32 + tid] : 0.f;
+    vs = warp_sum(vs); vb = warp_sum(vb);
+    if (tid == 0) { p.tile_energy[2 * tile] = vs; p.tile_energy[2 * tile + 1] = vb; }
+  }
+
+  float gh = p.gradH;
+  if (WITH_GRAD) {
+    if (p.gradH_dev) gh *= __ldg(p.gradH_dev);
+    // ---------------- phase 2: per-vertex gather ------------------------------------------------
+    for (int pidx = tid; pidx < td.ngrp * 32; pidx += NT) {
+      const int g = pidx >> 5, lane = pidx & 31;
+      const int beg = __ldg(p.ell_grp_ptr + td.grp_off + g), end = __ldg(p.ell_grp_ptr + td.grp_off + g + 1);
+      const uint16_t *ep = p.ell + size_t(td.ell_off) + beg + lane;
+      const int len = (end - beg) >> 5;
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < len; ++k) {
+        const unsigned en = __ldg(ep + k * 32);
+        if (en != 0xffffu) {
+          const float *o = outb + ((en & 7u) * 3) * TT + (en >> 3);
+          g0 += o[0]; g1 += o[TT]; g2 += o[2 * TT];
+        }
+      }
+      if (pidx < td.nvert) {
+        const int d = __ldg(p.dest + td.vert_off + pidx);
+        if (d >= 0) {
+          float *gp = p.grad + 3 * size_t(d);
+          gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
+        } else {
+          float *sp = p.scratch + 3 * size_t(-1 - d);
+          sp[0] = g0; sp[1] = g1; sp[2] = g2;
+        }
+      }
+    }
+  }
+
+  // ---------------- phase 3: last-arriver combines ----------------------------------------------
+  __threadfence();
+  __syncthreads();
+  const int ncg = WITH_GRAD ? td.ncg : 0;
+  for (int base = 0; base < ncg + 1; base += 32) {   // slot `ncg` is the energy group
+    if (tid < 32) {
+      const int q = base + tid;
+      int last = 0;
+      if (q < ncg) {
+        const int o = __ldg(p.cg_list + td.cg_off + q);
+        last = (atomicAdd(p.done + o, 1) == __ldg(p.need + o) - 1);
+      } else if (q == ncg) {
+        last = (atomicAdd(p.energy_counter, 1u) == uint32_t(p.n_tiles - 1));
+      }
+      s_flag[tid] = last;
+    }
+    __syncthreads();
+    for (int j = 0; j < 32 && base + j <= ncg; ++j) {
+      if (!s_flag[j]) continue;
+      __threadfence();
+      const int q = base + j;
+      if (q < ncg) {
+        const int o = __ldg(p.cg_list + td.cg_off + q);
+        const int s0 = __ldg(p.gsv_ptr + o), s1 = __ldg(p.gsv_ptr + o + 1);
+        for (int sv = s0 + tid; sv < s1; sv += NT) {
+          const int a0 = __ldg(p.sv_slot_ptr + sv), a1 = __ldg(p.sv_slot_ptr + sv + 1);
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+          for (int s = a0; s < a1; ++s) {
+            const float *sp = p.scratch + 3 * size_t(s);
+            g0 += __ldcg(sp); g1 += __ldcg(sp + 1); g2 += __ldcg(sp + 2);
+          }
+          float *gp = p.grad + 3 * size_t(__ldg(p.sv_vid + sv));
+          gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
+        }
+        if (tid == 0) p.done[o] = 0;
+      } else {
+        // fold the per-tile energies in a fixed order, fp64
+        double as = 0.0, ab = 0.0;
+        for (int t = tid; t < p.n_tiles; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
+        as = warp_sum(as); ab = warp_sum(ab);
+        __shared__ double s_dred[2 * (NT / 32)];
+        if ((tid & 31) == 0) { s_dred[tid >> 5] = as; s_dred[NT / 32 + (tid >> 5)] = ab; }
+        __syncthreads();
+        if (tid == 0) {
+          double ts = 0.0, tb = 0.0;
+          for (int wgt = 0; wgt < NT / 32; ++wgt) { ts += s_dred[wgt]; tb += s_dred[NT / 32 + wgt]; }
+          p.energy_out[0] = float(double(p.c1) * ts + double(p.c2) * tb);
+          p.energy_out[1] = float(ts);
+          p.energy_out[2] = float(tb);
+          *p.energy_counter = 0u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- level-1 helpers -------------------------------------------------------------------------------
+__global__ void scale_kernel(const float *__restrict__ g, int64_t count, float gradH, const float *gradH_dev,
+                             float *__restrict__ out) {
+  const float s = gradH * (gradH_dev ? __ldg(gradH_dev) : 1.f);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    out[i] = s * g[i];
+}
+
+__device__ __forceinline__ void block_max_to(float v, float *dst) {
+  // v >= 0.  Order-preserving uint compare for non-negative floats.
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ float s_m[32];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m = (threadIdx.x < (blockDim.x + 31) / 32) ? s_m[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int *>(dst), __float_as_uint(m));
+  }
+  __syncthreads();
+}
+
+__global__ void absmax_kernel(const float *__restrict__ g, int64_t count, float *work) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(g[i]));
+  block_max_to(m, work);
+}
+
+// if max|g| > thr: g *= s / max|g|.  Consumes and re-zeroes work[0] through a ticket in work[1].
+__global__ void grad_limit_apply_kernel(float *g, int64_t count, float thr, float s, float *work) {
+  const float m = __ldcg(work);
+  if (m > thr) {
+    const float f = s / m;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) g[i] *= f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(work + 1);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) { work[0] = 0.f; *ticket = 0u; }
+  }
+}
+
+// AdamUniform (utils/optimizer.py:37-89), pass 1: moments + the two global maxima.
+__global__ void adam_uniform_moments_kernel(const float *__restrict__ grad, float *__restrict__ g1, float *__restrict__ g2,
+                                            int64_t count, float b1, float b2, float inv_bc1, float inv_bc2, float *work) {
+  float mx2 = 0.f, mx1 = 0.f;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float g = grad[i];
+    const float m1 = b1 * g1[i] + (1.f - b1) * g;           // optimizer.py:61
+    const float m2 = b2 * g2[i] + (1.f - b2) * (g * g);     // optimizer.py:62
+    g1[i] = m1; g2[i] = m2;
+    mx2 = fmaxf(mx2, sqrtf(m2 * inv_bc2));                  // optimizer.py:68,74
+    mx1 = fmaxf(mx1, fabsf(m1 * inv_bc1));                  // optimizer.py:67,83
+  }
+  block_max_to(mx2, work);
+  block_max_to(mx1, work + 1);
+}
+
+// pass 2: p -= lr * clamp(m1_hat / (1e-8 + max sqrt(m2_hat)))   (optimizer.py:74-88)
+__global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__restrict__ g1, int64_t count, float lr,
+                                          float inv_bc1, float grad_limit, float *work, unsigned int *ticket) {
+  const float denom = 1e-8f + __ldcg(work);
+  float f = inv_bc1 / denom;
+  if (grad_limit > 0.f) {
+    const float s = __ldcg(work + 1) / denom;               // max |gr|
+    if (s > grad_limit) f *= grad_limit / s;
+  }
+  f *= lr;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) p[i] -= f * g1[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) { work[0] = 0.f; work[1] = 0.f; *ticket = 0u; }
+  }
+}
+
+template <int TT, int NVMAX, int NT>
+cudaError_t launch_variant(const KParams &p, cudaStream_t stream) {
+  const int smem = Smem<TT, NVMAX>::kBytes;
+  if (p.grad) energy_grad_kernel<TT, NVMAX, NT, true><<<p.n_tiles, NT, smem, stream>>>(p);
+  else energy_grad_kernel<TT, NVMAX, NT, false><<<p.n_tiles, NT, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int TT, int NVMAX, int NT>
+cudaError_t prepare_variant() {
+  const int smem = Smem<TT, NVMAX>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NVMAX, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(energy_grad_kernel<TT, NVMAX, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+inline int grid_for(int64_t count, int block) {
+  int64_t g = (count + block - 1) / block;
+  return int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+}  // namespace
+
+// Compiled (tile_tets -> staged-vertex capacity) variants.
+int nvmax_for(int tile_tets) {
+  switch (tile_tets) {
+    case 256: return 384;
+    case 512: return 640;
+    case 1024: return 1152;
+  }
+  return 0;
+}
+
+bool variant_supported(int tile_tets, int max_local_vertices) {
+  return nvmax_for(tile_tets) != 0 && max_local_vertices == nvmax_for(tile_tets);
+}
+
+static int g_threads_512 = 256;
+
+cudaError_t prepare_energy_grad(int tile_tets, int) {
+  switch (tile_tets) {
+    case 256: return prepare_variant<256, 384, 256>();
+    case 512: {
+      cudaError_t e = prepare_variant<512, 640, 256>();
+      if (e != cudaSuccess) return e;
+      return prepare_variant<512, 640, 512>();
+    }
+    case 1024: return prepare_variant<1024, 1152, 512>();
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int, cudaStream_t stream) {
+  switch (tile_tets) {
+    case 256: return launch_variant<256, 384, 256>(p, stream);
+    case 512: return g_threads_512 == 512 ? launch_variant<512, 640, 512>(p, stream) : launch_variant<512, 640, 256>(p, stream);
+    case 1024: return launch_variant<1024, 1152, 512>(p, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+void set_threads_512(int nt) { g_threads_512 = (nt == 512) ? 512 : 256; }
+
+cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s) {
+  scale_kernel<<<grid_for(count, 256), 256, 0, s>>>(g, count, gradH, gradH_dev, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st) {
+  const int grid = grid_for(count, 256);
+  absmax_kernel<<<grid, 256, 0, st>>>(g, count, work2);
+  grad_limit_apply_kernel<<<grid, 256, 0, st>>>(g, count, thr, s, work2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, float lr, float b1,
+                                float b2, int step, float grad_limit, float *work, cudaStream_t st) {
+  const float inv_bc1 = float(1.0 / (1.0 - pow(double(b1), double(step))));   // optimizer.py:67
+  const float inv_bc2 = float(1.0 / (1.0 - pow(double(b2), double(step))));   // optimizer.py:68
+  const int grid = grid_for(count, 256);
+  adam_uniform_moments_kernel<<<grid, 256, 0, st>>>(grad, g1, g2, count, b1, b2, inv_bc1, inv_bc2, work);
+  adam_uniform_apply_kernel<<<grid, 256, 0, st>>>(p, g1, count, lr, inv_bc1, grad_limit, work, reinterpret_cast<unsigned int *>(work + 2));
+  return cudaGetLastError();
+}
+
+}  // namespace tsb

@@ -1,0 +1,334 @@
+// Host plan builder: rest inverses, face adjacency, locality-ordered tiles, per-tile vertex
+// staging lists, gather tables and the shared-vertex combine lists.  See tsb_plan.h.
+#include "tsb_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/tssplat_b200.h"
+
+namespace tsb {
+namespace {
+
+struct FaceKey {
+  uint32_t a, b, c, owner;  // sorted vertex triple; owner = 4*tet + local face
+  bool operator<(const FaceKey &o) const {
+    if (a != o.a) return a < o.a;
+    if (b != o.b) return b < o.b;
+    return c < o.c;
+  }
+  bool same(const FaceKey &o) const { return a == o.a && b == o.b && c == o.c; }
+};
+
+// Face k of a tet is the face opposite to local vertex k.
+const int kFace[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
+
+inline uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000FF;
+  v = (v | (v << 8)) & 0x0300F00F;
+  v = (v | (v << 4)) & 0x030C30C3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+
+struct UnionFind {
+  std::vector<int32_t> p;
+  explicit UnionFind(int n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+  int find(int x) {
+    while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+    return x;
+  }
+  void unite(int a, int b) {
+    a = find(a); b = find(b);
+    if (a != b) p[std::max(a, b)] = std::min(a, b);
+  }
+};
+
+bool invert3(const double *m, double *o) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double d = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  if (d == 0.0 || !std::isfinite(d)) return false;
+  const double id = 1.0 / d;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+
+}  // namespace
+
+int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, const PlanOptions &opt,
+               HostPlan &P, std::string &err) {
+  if (!rest || !tets || n <= 0 || nele <= 0) { err = "null input or non-positive size"; return TSB_E_INVALID; }
+  const int TT = opt.tile_tets, NVMAX = opt.max_local_vertices;
+  if (TT < 32 || TT > 4096 || (TT % 32) != 0 || NVMAX < 8 || NVMAX > 0xFFFE) {
+    err = "tile_tets must be a multiple of 32 in [32,4096]";
+    return TSB_E_INVALID;
+  }
+  P = HostPlan();
+  P.n = n; P.nele = nele; P.tile_tets = TT; P.max_local_vertices = NVMAX; P.laplacian_scale = opt.laplacian_scale;
+
+  // ---- validate, rest inverses (fp64 -> fp32 like the reference: tet_spheres.cpp:43-45) --------
+  std::vector<float> Binv(size_t(nele) * 9);
+  for (int t = 0; t < nele; ++t) {
+    const int32_t *v = tets + 4 * size_t(t);
+    for (int k = 0; k < 4; ++k)
+      if (v[k] < 0 || v[k] >= n) { err = "tet " + std::to_string(t) + " has a vertex index out of range"; return TSB_E_MESH; }
+    if (v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3]) {
+      err = "tet " + std::to_string(t) + " repeats a vertex"; return TSB_E_MESH;
+    }
+    double Dm[9], Bi[9];
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) Dm[3 * r + k] = double(rest[3 * size_t(v[k + 1]) + r]) - double(rest[3 * size_t(v[0]) + r]);
+    if (!invert3(Dm, Bi)) { err = "tet " + std::to_string(t) + " has zero rest volume"; return TSB_E_MESH; }
+    for (int i = 0; i < 9; ++i) Binv[size_t(t) * 9 + i] = float(Bi[i]);
+  }
+
+  // ---- face adjacency -> opposite vertex across each face ---------------------------------------
+  std::vector<int32_t> opp(size_t(nele) * 4, -1);  // global id of the neighbour's vertex not on the shared face
+  UnionFind uf(n);
+  {
+    std::vector<FaceKey> fk(size_t(nele) * 4);
+    for (int t = 0; t < nele; ++t) {
+      const int32_t *v = tets + 4 * size_t(t);
+      uf.unite(v[0], v[1]); uf.unite(v[0], v[2]); uf.unite(v[0], v[3]);
+      for (int k = 0; k < 4; ++k) {
+        uint32_t f[3] = {uint32_t(v[kFace[k][0]]), uint32_t(v[kFace[k][1]]), uint32_t(v[kFace[k][2]])};
+        if (f[0] > f[1]) std::swap(f[0], f[1]);
+        if (f[1] > f[2]) std::swap(f[1], f[2]);
+        if (f[0] > f[1]) std::swap(f[0], f[1]);
+        fk[4 * size_t(t) + k] = FaceKey{f[0], f[1], f[2], uint32_t(4 * t + k)};
+      }
+    }
+    std::sort(fk.begin(), fk.end());
+    const size_t nf = fk.size();
+    for (size_t i = 0; i < nf;) {
+      size_t j = i + 1;
+      while (j < nf && fk[j].same(fk[i])) ++j;
+      if (j - i > 2) { err = "non-manifold mesh: a face is shared by more than two tets"; return TSB_E_MESH; }
+      if (j - i == 2) {
+        const uint32_t o0 = fk[i].owner, o1 = fk[i + 1].owner;
+        opp[o0] = tets[o1];  // tets[4*t1 + k1] is the vertex of t1 opposite the shared face
+        opp[o1] = tets[o0];
+      } else {
+        ++P.n_boundary_faces;
+      }
+      i = j;
+    }
+  }
+
+  // ---- locality order: (component, Morton code of the rest centroid inside the component bbox) --
+  std::vector<int32_t> comp_of_vertex(n);
+  {
+    std::vector<int32_t> label(n, -1);
+    int32_t nc = 0;
+    for (int v = 0; v < n; ++v) {
+      const int r = uf.find(v);
+      if (label[r] < 0) label[r] = nc++;
+      comp_of_vertex[v] = label[r];
+    }
+    P.n_components = nc;
+  }
+  const int NC = P.n_components;
+  std::vector<float> lo(size_t(NC) * 3, 3.0e38f), hi(size_t(NC) * 3, -3.0e38f);
+  for (int v = 0; v < n; ++v) {
+    const int c = comp_of_vertex[v];
+    for (int r = 0; r < 3; ++r) {
+      lo[3 * size_t(c) + r] = std::min(lo[3 * size_t(c) + r], rest[3 * size_t(v) + r]);
+      hi[3 * size_t(c) + r] = std::max(hi[3 * size_t(c) + r], rest[3 * size_t(v) + r]);
+    }
+  }
+  std::vector<uint64_t> key(nele);
+  for (int t = 0; t < nele; ++t) {
+    const int32_t *v = tets + 4 * size_t(t);
+    const int c = comp_of_vertex[v[0]];
+    uint32_t q[3];
+    for (int r = 0; r < 3; ++r) {
+      const float cen = 0.25f * (rest[3 * size_t(v[0]) + r] + rest[3 * size_t(v[1]) + r] + rest[3 * size_t(v[2]) + r] + rest[3 * size_t(v[3]) + r]);
+      const float ext = hi[3 * size_t(c) + r] - lo[3 * size_t(c) + r];
+      float u = ext > 0.f ? (cen - lo[3 * size_t(c) + r]) / ext : 0.f;
+      u = std::min(std::max(u, 0.f), 1.f);
+      q[r] = uint32_t(u * 1023.f);
+    }
+    const uint32_t m = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+    key[t] = (uint64_t(uint32_t(c)) << 32) | m;
+  }
+  P.tet_order.resize(nele);
+  std::iota(P.tet_order.begin(), P.tet_order.end(), 0);
+  std::stable_sort(P.tet_order.begin(), P.tet_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+
+  // ---- greedy tiling: up to TT tets and NVMAX staged vertices per tile -----------------------------
+  std::vector<int32_t> tile_first;  // position in tet_order of each tile's first tet (+ sentinel)
+  {
+    std::vector<int32_t> stamp(n, -1);
+    int cur_tets = 0, cur_verts = 0, tile = 0;
+    tile_first.push_back(0);
+    for (int pos = 0; pos < nele; ++pos) {
+      const int t = P.tet_order[pos];
+      int32_t st[8];
+      for (int k = 0; k < 4; ++k) { st[k] = tets[4 * size_t(t) + k]; st[4 + k] = opp[4 * size_t(t) + k]; }
+      int add = 0;
+      for (int k = 0; k < 8; ++k) {
+        if (st[k] < 0 || stamp[st[k]] == tile) continue;
+        bool dup = false;
+        for (int j = 0; j < k; ++j) dup |= (st[j] == st[k]);
+        add += !dup;
+      }
+      if (cur_tets == TT || cur_verts + add > NVMAX) {
+        ++tile; tile_first.push_back(pos); cur_tets = 0; cur_verts = 0;
+        add = 0;
+        for (int k = 0; k < 8; ++k) {
+          if (st[k] < 0) continue;
+          bool dup = false;
+          for (int j = 0; j < k; ++j) dup |= (st[j] == st[k]);
+          add += !dup;
+        }
+      }
+      for (int k = 0; k < 8; ++k) if (st[k] >= 0) stamp[st[k]] = tile;
+      cur_tets += 1; cur_verts += add;
+    }
+    tile_first.push_back(nele);
+  }
+  const int NTILE = int(tile_first.size()) - 1;
+  P.n_tiles = NTILE;
+  P.tiles.resize(NTILE);
+  P.idx8.assign(size_t(NTILE) * TT * 8, 0xFFFF);
+  P.Bsoa.assign(size_t(NTILE) * 9 * TT, 0.f);
+
+  // ---- per tile: staged vertex list (id-sorted), local stencil ids ----------------------------
+  std::vector<int32_t> local_of(n, -1);
+  std::vector<std::vector<int32_t>> tile_verts(NTILE);
+  for (int tile = 0; tile < NTILE; ++tile) {
+    const int p0 = tile_first[tile], p1 = tile_first[tile + 1];
+    std::vector<int32_t> &vs = tile_verts[tile];
+    vs.reserve(size_t(p1 - p0));
+    for (int pos = p0; pos < p1; ++pos) {
+      const int t = P.tet_order[pos];
+      for (int k = 0; k < 4; ++k) {
+        vs.push_back(tets[4 * size_t(t) + k]);
+        if (opp[4 * size_t(t) + k] >= 0) vs.push_back(opp[4 * size_t(t) + k]);
+      }
+    }
+    std::sort(vs.begin(), vs.end());
+    vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
+    for (size_t i = 0; i < vs.size(); ++i) local_of[vs[i]] = int32_t(i);
+    TileDesc &td = P.tiles[tile];
+    td.ntet = p1 - p0;
+    td.nvert = int32_t(vs.size());
+    td.vert_off = int32_t(P.n_local_vertices);
+    P.n_local_vertices += td.nvert;
+    for (int pos = p0; pos < p1; ++pos) {
+      const int t = P.tet_order[pos], lt = pos - p0;
+      uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+      for (int k = 0; k < 4; ++k) {
+        d[k] = uint16_t(local_of[tets[4 * size_t(t) + k]]);
+        const int32_t o = opp[4 * size_t(t) + k];
+        d[4 + k] = o >= 0 ? uint16_t(local_of[o]) : uint16_t(0xFFFF);
+      }
+      for (int i = 0; i < 9; ++i) P.Bsoa[(size_t(tile) * 9 + i) * TT + lt] = Binv[size_t(t) * 9 + i];
+    }
+  }
+  if (P.n_local_vertices > int64_t(0x7fffffff) - 64) { err = "mesh too large for 32-bit staging offsets"; return TSB_E_INVALID; }
+
+  // ---- vertex -> touching tiles (ascending tile id), shared vertices, owners, scratch slots -----
+  std::vector<int32_t> touch_ptr(size_t(n) + 1, 0);
+  for (int tile = 0; tile < NTILE; ++tile)
+    for (int32_t v : tile_verts[tile]) touch_ptr[size_t(v) + 1]++;
+  for (int v = 0; v < n; ++v) touch_ptr[size_t(v) + 1] += touch_ptr[v];
+  std::vector<int32_t> touch(size_t(touch_ptr[n]));
+  {
+    std::vector<int32_t> cur(touch_ptr.begin(), touch_ptr.end() - 1);
+    for (int tile = 0; tile < NTILE; ++tile)
+      for (int32_t v : tile_verts[tile]) touch[size_t(cur[v]++)] = tile;
+  }
+  // shared vertices ordered by (owner tile, vertex id); owner = lowest touching tile
+  std::vector<int32_t> shared;
+  for (int v = 0; v < n; ++v)
+    if (touch_ptr[size_t(v) + 1] - touch_ptr[v] > 1) shared.push_back(v);
+  std::stable_sort(shared.begin(), shared.end(), [&](int32_t a, int32_t b) { return touch[touch_ptr[a]] < touch[touch_ptr[b]]; });
+  P.n_shared_vertices = int32_t(shared.size());
+  P.sv_vid = shared;
+  P.sv_slot_ptr.assign(shared.size() + 1, 0);
+  P.gsv_ptr.assign(size_t(NTILE) + 1, 0);
+  std::vector<int32_t> sv_of(n, -1);
+  for (size_t s = 0; s < shared.size(); ++s) {
+    const int32_t v = shared[s];
+    sv_of[v] = int32_t(s);
+    P.sv_slot_ptr[s + 1] = P.sv_slot_ptr[s] + (touch_ptr[size_t(v) + 1] - touch_ptr[v]);
+    P.gsv_ptr[size_t(touch[touch_ptr[v]]) + 1]++;
+  }
+  for (int tile = 0; tile < NTILE; ++tile) P.gsv_ptr[size_t(tile) + 1] += P.gsv_ptr[tile];
+  P.n_slots = P.sv_slot_ptr[shared.size()];
+
+  // ---- per tile: staging arrays, gather table, contribution groups -----------------------------
+  P.vlist.resize(size_t(P.n_local_vertices));
+  P.Xloc.resize(size_t(P.n_local_vertices) * 3);
+  P.dest.resize(size_t(P.n_local_vertices));
+  P.need.assign(NTILE, 0);
+  std::vector<int32_t> deg, order_v, fill;
+  for (int tile = 0; tile < NTILE; ++tile) {
+    TileDesc &td = P.tiles[tile];
+    const std::vector<int32_t> &vs = tile_verts[tile];
+    const int nv = td.nvert;
+    for (int i = 0; i < nv; ++i) {
+      P.vlist[size_t(td.vert_off) + i] = vs[i];
+      for (int r = 0; r < 3; ++r) P.Xloc[3 * (size_t(td.vert_off) + i) + r] = rest[3 * size_t(vs[i]) + r];
+    }
+    // in-tile degree of each staged vertex (number of (tet, slot) entries that add into it)
+    deg.assign(nv, 0);
+    for (int lt = 0; lt < td.ntet; ++lt) {
+      const uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+      for (int s = 0; s < 8; ++s) if (d[s] != 0xFFFF) deg[d[s]]++;
+    }
+    order_v.resize(nv);
+    std::iota(order_v.begin(), order_v.end(), 0);
+    std::stable_sort(order_v.begin(), order_v.end(), [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
+    std::vector<int32_t> slot_of_local(nv);  // local vertex -> position in the gather table
+    for (int p = 0; p < nv; ++p) slot_of_local[order_v[p]] = p;
+    td.ngrp = (nv + 31) / 32;
+    td.grp_off = int32_t(P.ell_grp_ptr.size());
+    td.ell_off = int32_t(P.ell.size());
+    int32_t rel = 0;
+    for (int g = 0; g < td.ngrp; ++g) {
+      P.ell_grp_ptr.push_back(rel);
+      rel += 32 * deg[order_v[size_t(g) * 32]];  // group length = its first (largest) degree
+    }
+    P.ell_grp_ptr.push_back(rel);
+    if (size_t(td.ell_off) + size_t(rel) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
+    P.ell.resize(size_t(td.ell_off) + size_t(rel), 0xFFFF);
+    fill.assign(nv, 0);
+    for (int lt = 0; lt < td.ntet; ++lt) {
+      const uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+      for (int s = 0; s < 8; ++s) {
+        if (d[s] == 0xFFFF) continue;
+        const int p = slot_of_local[d[s]], g = p >> 5, lane = p & 31;
+        const size_t base = size_t(td.ell_off) + size_t(P.ell_grp_ptr[size_t(td.grp_off) + g]);
+        P.ell[base + size_t(fill[p]++) * 32 + lane] = uint16_t(lt * 8 + s);
+      }
+    }
+    // destinations + owner groups
+    td.cg_off = int32_t(P.cg_list.size());
+    for (int p = 0; p < nv; ++p) {
+      const int32_t v = vs[order_v[p]];
+      const int32_t s = sv_of[v];
+      if (s < 0) {
+        P.dest[size_t(td.vert_off) + p] = v;
+      } else {
+        const int32_t *tb = &touch[touch_ptr[v]], *te = &touch[touch_ptr[size_t(v) + 1]];
+        const int rank = int(std::lower_bound(tb, te, tile) - tb);
+        P.dest[size_t(td.vert_off) + p] = -1 - (P.sv_slot_ptr[s] + rank);
+        const int32_t owner = tb[0];
+        bool seen = false;
+        for (size_t q = size_t(td.cg_off); q < P.cg_list.size(); ++q) seen |= (P.cg_list[q] == owner);
+        if (!seen) { P.cg_list.push_back(owner); P.need[owner]++; }
+      }
+    }
+    td.ncg = int32_t(P.cg_list.size()) - td.cg_off;
+  }
+  return TSB_OK;
+}
+
+}  // namespace tsb

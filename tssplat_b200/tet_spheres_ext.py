@@ -1,0 +1,188 @@
+"""Drop-in for the reference's ``tet_spheres_ext`` pybind11 module
+(``tssplat_ext/tet_spheres/tet_spheres.cpp:225-266``): same names, same argument meaning.
+
+    from tet_spheres import tet_spheres_ext        # energies/smooth_barrier.py:6, unchanged
+    tet_sp = tet_spheres_ext.TetSpheres(v_flat, f_flat)
+    e = tet_spheres_ext.forward(x, tet_sp, c1, c2, order)
+    g = tet_spheres_ext.backward(grad_output, x, tet_sp, c1, c2, order)
+
+Underneath: one sm_100a kernel launch through the C ABI (``include/tssplat_b200.h``) computes the
+energy AND the gradient; ``backward`` only rescales the cached gradient by ``grad_output``.
+PyTorch is used for device memory and the current stream, nothing else.
+
+Deliberate differences from the reference, all on error / sync behaviour:
+
+* ``forward`` returns a 0-dim tensor on ``x``'s device instead of a CPU scalar
+  (``tet_spheres_cuda.cu:194``) -- no host sync.  Set ``return_cpu_scalar = True`` for the
+  reference's behaviour.
+* bad constructor input raises ``RuntimeError`` instead of printing to stderr and returning a
+  half-constructed object (``tet_spheres.cpp:240,249``).
+* ``order`` outside {2,4} raises instead of silently returning zeros (``tet_spheres_cuda.cu:57-63``).
+* ``grad_limit`` does what it was meant to (scale by the arg-max magnitude), silently.
+* no module-import side effect (``pgo_init`` + "initializing" print, ``tet_spheres.cpp:14-30``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from .mesh import load_veg
+
+__all__ = ["TetSpheres", "forward", "backward", "random_x", "grad_limit"]
+
+return_cpu_scalar = False
+#: compute the gradient inside ``forward`` (one launch per iteration) when ``x.requires_grad``
+fuse_backward_into_forward = True
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class TetSpheres:
+    """State object (replaces ``struct TetSpheres``, ``tet_spheres.h:24-42``).
+
+    ``TetSpheres(vertices, elements)``: ``vertices`` 1-D C-contiguous float32 of length 3n (REST
+    positions), ``elements`` 1-D C-contiguous int32 of length 4*nele, 0-based
+    (``tet_spheres.cpp:234-258``).  ``TetSpheres(filename)`` loads a ``.veg`` file
+    (``tet_spheres.cpp:108-117``).
+    """
+
+    def __init__(self, vertices, elements=None, *, device=None, tile_tets: int = 0,
+                 laplacian_scale: int = 0):
+        self._h = None
+        if isinstance(vertices, (str, bytes)) and elements is None:
+            v, t = load_veg(vertices if isinstance(vertices, str) else vertices.decode())
+            vertices = v.astype(np.float32).reshape(-1)
+            elements = t.astype(np.int32).reshape(-1)
+        if elements is None:
+            raise RuntimeError("TetSpheres(vertices, elements): elements missing")
+        vertices = np.asarray(vertices)
+        elements = np.asarray(elements)
+        if vertices.ndim != 1 or vertices.dtype != np.float32:
+            raise RuntimeError(f"Wrong vertex type:{vertices.ndim},{vertices.dtype} (need 1-D float32)")
+        if elements.ndim != 1 or elements.dtype != np.int32:
+            raise RuntimeError(f"Wrong tet type:{elements.ndim},{elements.dtype} (need 1-D int32)")
+        if vertices.size % 3 or elements.size % 4:
+            raise RuntimeError("vertices must have 3n entries and elements 4*nele entries")
+        vertices = np.ascontiguousarray(vertices)
+        elements = np.ascontiguousarray(elements)
+        if not torch.cuda.is_available():
+            raise RuntimeError("tet_spheres_ext needs a CUDA device (B200); there is no CPU path")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("tet_spheres_ext needs a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        torch.cuda.init()
+        opt = _capi.tsb_options_t(tile_tets=int(tile_tets), laplacian_scale=int(laplacian_scale))
+        h = C.c_void_p()
+        rc = _capi.lib.tsb_create(vertices.ctypes.data, elements.ctypes.data, vertices.size // 3,
+                                  elements.size // 4, C.byref(opt), self.device.index, C.byref(h))
+        _capi.check(rc, None, "TetSpheres")
+        self._h = h
+        info = _capi.tsb_info_t()
+        _capi.check(_capi.lib.tsb_get_info(self._h, C.byref(info)), self._h, "TetSpheres")
+        self.info = {k: getattr(info, k) for k, _ in _capi.tsb_info_t._fields_}
+        self.n = int(info.n)
+        self.nele = int(info.nele)
+        self.n3 = 3 * self.n
+        self._cache_key = None
+        self._cache_grad: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _capi.lib.tsb_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+
+    # ------------------------------------------------------------------------------------------
+    def _check_x(self, x: torch.Tensor) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor) or x.dtype != torch.float32 or not x.is_cuda:
+            raise RuntimeError("vertexPositions must be a float32 CUDA tensor")
+        if x.device != self.device:
+            raise RuntimeError(f"vertexPositions is on {x.device}, TetSpheres on {self.device}")
+        if x.numel() != self.n3:
+            raise RuntimeError(f"vertexPositions has {x.numel()} entries, expected {self.n3}")
+        return x.detach().contiguous()            # tet_spheres_cuda.cu:124
+
+    def energy_grad(self, x: torch.Tensor, c1: float, c2: float, order: int, gradH=1.0,
+                    want_grad: bool = True):
+        """The fused launch.  Returns (energy[3] = total/smooth/barrier on device, grad or None)."""
+        xc = self._check_x(x)
+        energy = torch.empty(3, dtype=torch.float32, device=self.device)
+        grad = torch.empty((self.n, 3), dtype=torch.float32, device=self.device) if want_grad else None
+        gh_val, gh_ptr, keep = 1.0, None, None
+        if isinstance(gradH, torch.Tensor):
+            if gradH.is_cuda:
+                keep = gradH.detach().to(device=self.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
+                gh_ptr = keep.data_ptr()
+            else:
+                gh_val = float(gradH)
+        else:
+            gh_val = float(gradH)
+        rc = _capi.lib.tsb_energy_grad(self._h, xc.data_ptr(), float(c1), float(c2), int(order), gh_val,
+                                       gh_ptr, energy.data_ptr(), grad.data_ptr() if want_grad else None,
+                                       _stream_ptr(self.device))
+        _capi.check(rc, self._h, "tet_spheres_ext")
+        del keep
+        return energy, grad
+
+
+def _key(x: torch.Tensor, c1, c2, order):
+    return (x.data_ptr(), x._version, tuple(x.shape), float(c1), float(c2), int(order))
+
+
+def forward(vertexPositions: torch.Tensor, tet_sp: TetSpheres, c1: float, c2: float, order: int) -> torch.Tensor:
+    """``E = c1 * 1/2 x^T G^T L^T L G x + c2 * sum_t max(-det F_t, 0)^order`` as a 0-dim tensor
+    (``tet_spheres.cpp:208-211``, ``tet_spheres_cuda.cu:118-195``)."""
+    want = bool(fuse_backward_into_forward and vertexPositions.requires_grad)
+    energy, grad = tet_sp.energy_grad(vertexPositions, c1, c2, order, 1.0, want_grad=want)
+    if want:
+        tet_sp._cache_key, tet_sp._cache_grad = _key(vertexPositions, c1, c2, order), grad
+    else:
+        tet_sp._cache_key, tet_sp._cache_grad = None, None
+    e = energy[0]
+    return e.cpu() if return_cpu_scalar else e
+
+
+def backward(gradH, vertexPositions: torch.Tensor, tet_sp: TetSpheres, c1: float, c2: float, order: int) -> torch.Tensor:
+    """``gradH * dE/dx`` as a fresh [n,3] fp32 tensor on ``x``'s device
+    (``tet_spheres.cpp:213-216``, ``tet_spheres_cuda.cu:197-263``)."""
+    shape = tuple(vertexPositions.shape)
+    if tet_sp._cache_grad is not None and tet_sp._cache_key == _key(vertexPositions, c1, c2, order):
+        g = tet_sp._cache_grad
+        out = torch.empty_like(g)
+        gh_val, gh_ptr, keep = 1.0, None, None
+        if isinstance(gradH, torch.Tensor) and gradH.is_cuda:
+            keep = gradH.detach().to(device=g.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
+            gh_ptr = keep.data_ptr()
+        else:
+            gh_val = float(gradH)
+        rc = _capi.lib.tsb_scale(g.data_ptr(), g.numel(), gh_val, gh_ptr, out.data_ptr(), _stream_ptr(g.device))
+        _capi.check(rc, None, "tet_spheres_ext.backward")
+        del keep
+    else:
+        _, out = tet_sp.energy_grad(vertexPositions, c1, c2, order, gradH, want_grad=True)
+    return out.reshape(shape) if len(shape) == 2 else out
+
+
+def random_x(tet_sp: TetSpheres) -> torch.Tensor:
+    """``torch.rand({n, 3})`` on the CPU (``tet_spheres.cpp:218-221``)."""
+    return torch.rand((tet_sp.n, 3))
+
+
+def grad_limit(grad: torch.Tensor, s_threshold: float, s: float) -> None:
+    """In place: if ``max|grad| > s_threshold`` scale ``grad`` so that its max magnitude is ``s``
+    (the intent of ``tet_spheres_cuda.cu:265-303``)."""
+    if not grad.is_cuda or grad.dtype != torch.float32 or not grad.is_contiguous():
+        raise RuntimeError("grad_limit needs a contiguous float32 CUDA tensor")
+    with torch.cuda.device(grad.device):
+        rc = _capi.lib.tsb_grad_limit(grad.data_ptr(), grad.numel(), float(s_threshold), float(s),
+                                      _stream_ptr(grad.device))
+    _capi.check(rc, None, "tet_spheres_ext.grad_limit")
