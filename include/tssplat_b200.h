@@ -51,6 +51,8 @@ typedef struct {
   int64_t stream_bytes;     /* bytes one launch reads+writes from the handle's arrays + x + grad */
   int32_t n_boundary_faces;
   int32_t max_local_vertices;
+  int32_t fill;             /* tets per tile actually used (<= tile_tets; wave-balanced)         */
+  int32_t reserved;
 } tsb_info_t;
 
 /* Replaces TetSpheres::TetSpheres(int nv, double*, int ntet, int*) + TetSpheres::init

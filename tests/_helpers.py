@@ -44,20 +44,22 @@ class COracle:
         return float(c1) * terms[0] + float(c2) * terms[1], terms, g
 
 
-_TILE_DT = np.dtype([(k, np.int32) for k in
-                     ("ntet", "nvert", "vert_off", "ngrp", "grp_off", "ell_off", "cg_off", "ncg")])
-_ARRAYS = {"tiles": _TILE_DT, "idx8": np.uint16, "Bsoa": np.float32, "vlist": np.int32, "Xloc": np.float32,
-           "dest": np.int32, "ell": np.uint16, "ell_grp_ptr": np.int32, "cg_list": np.int32, "need": np.int32,
-           "gsv_ptr": np.int32, "sv_vid": np.int32, "sv_slot_ptr": np.int32, "tet_order": np.int32}
+_ARRAYS = {"vblob": np.uint8, "tblob": np.uint8, "ell": np.uint16, "cg": np.int32, "sv_rec": np.int32,
+           "need": np.int32, "gsv_ptr": np.int32, "tet_order": np.int32, "tile_first": np.int32}
+_HDR = ("ntet", "nvert", "ngrp", "ncg", "cg_off", "ell_off", "nell")
 
 
-def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0):
+def vblob_bytes(nv):
+    return 64 + 20 * nv + 4 * (nv // 32 + 4)
+
+
+def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0):
     """Run the product's host plan builder (no CUDA) and copy its arrays out as numpy."""
     from tssplat_b200 import _capi
     lib = _capi.lib
     lib.tsb_debug_plan_build.restype = C.c_int
     lib.tsb_debug_plan_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                         C.POINTER(C.c_void_p)]
+                                         C.c_int32, C.POINTER(C.c_void_p)]
     lib.tsb_debug_plan_array.restype = C.c_int
     lib.tsb_debug_plan_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int32)]
@@ -67,7 +69,7 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0):
     tets = np.ascontiguousarray(np.asarray(tets, dtype=np.int32).reshape(-1))
     d = C.c_void_p()
     rc = lib.tsb_debug_plan_build(rest.ctypes.data, tets.ctypes.data, rest.size // 3, tets.size // 4,
-                                  int(tile_tets), int(laplacian_scale), C.byref(d))
+                                  int(tile_tets), int(laplacian_scale), int(balance_sms), C.byref(d))
     if rc != 0:
         raise RuntimeError(_capi.last_error(None))
     try:
@@ -78,14 +80,33 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0):
             nbytes = cnt.value * eb.value
             buf = (C.c_char * nbytes).from_address(ptr.value) if nbytes else b""
             plan[name] = np.frombuffer(bytes(buf), dtype=dt).copy()
-        sc = np.zeros(8, np.int32)
+        sc = np.zeros(10, np.int32)
         lib.tsb_debug_plan_scalars(d, sc.ctypes.data)
         for k, v in zip(("n", "nele", "tile_tets", "max_local_vertices", "n_tiles", "n_components",
-                         "n_shared_vertices", "n_slots"), sc):
+                         "n_shared_vertices", "n_slots", "fill", "ell_cap"), sc):
             plan[k] = int(v)
         plan["laplacian_scale"] = int(laplacian_scale)
     finally:
         lib.tsb_debug_plan_free(d)
+    # unpack the per-tile blobs
+    TT, NV = plan["tile_tets"], plan["max_local_vertices"]
+    VB, TB = vblob_bytes(NV), 52 * TT
+    tiles = []
+    for t in range(plan["n_tiles"]):
+        vb = plan["vblob"][t * VB:(t + 1) * VB]
+        tb = plan["tblob"][t * TB:(t + 1) * TB]
+        hdr = dict(zip(_HDR, vb[:28].view(np.int32)))
+        nv, nt = int(hdr["nvert"]), int(hdr["ntet"])
+        tiles.append(dict(
+            hdr, vlist=vb[64:64 + 4 * NV].view(np.int32)[:nv],
+            X=np.stack([vb[64 + 4 * NV:64 + 8 * NV].view(np.float32)[:nv],
+                        vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 0],
+                        vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 1]], axis=1),
+            dest=vb[64 + 16 * NV:64 + 20 * NV].view(np.int32)[:nv],
+            grp_ptr=vb[64 + 20 * NV:].view(np.int32)[:int(hdr["ngrp"]) + 1],
+            idx8=tb[:16 * TT].view(np.uint16).reshape(-1, 8)[:nt],
+            B=tb[16 * TT:].view(np.float32).reshape(-1, 9)[:nt]))
+    plan["tiles"] = tiles
     return plan
 
 
@@ -97,18 +118,20 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
     n = plan["n"]
     grad = np.full((n, 3), np.nan, dtype=dtype)
     scratch = np.full((max(plan["n_slots"], 1), 3), np.nan, dtype=dtype)
-    idx8 = plan["idx8"].reshape(-1, 8)
-    Bs = plan["Bsoa"].reshape(-1, 9, TT)
     es_tot = eb_tot = 0.0
+    sv_rec = plan["sv_rec"].reshape(-1, 4)
     for ti, td in enumerate(plan["tiles"]):
-        nt, nv, vo = int(td["ntet"]), int(td["nvert"]), int(td["vert_off"])
-        vl = plan["vlist"][vo:vo + nv]
+        nt, nv = int(td["ntet"]), int(td["nvert"])
+        vl = td["vlist"]
         xs = x[vl]                                              # phase 0
-        Xs = plan["Xloc"].reshape(-1, 3)[vo:vo + nv].astype(dtype)
-        ids = idx8[ti * TT: ti * TT + nt].astype(np.int64)
-        own, opp = ids[:, :4], ids[:, 4:]
-        assert own.max() < nv
-        B = np.transpose(Bs[ti, :, :nt], (1, 0)).reshape(nt, 3, 3).astype(dtype)   # rows a1..a3
+        Xs = td["X"].astype(dtype)
+        ids = td["idx8"].astype(np.int64)
+        own, oppr = ids[:, :4], ids[:, 4:]
+        valid = (oppr & 0x8000) != 0
+        opp = oppr & 0x7FFF
+        assert own.max() < nv and opp.max() < nv
+        assert np.all(opp[~valid] == own[~valid]), "boundary faces must point at the own vertex"
+        B = td["B"].reshape(nt, 3, 3).astype(dtype)             # rows a1..a3
         a = np.concatenate([-B.sum(axis=1, keepdims=True), B], axis=1)              # nt x 4 x 3
         p = xs[own]                                             # nt x 4 x 3
         e = p[:, 1:, :] - p[:, :1, :]                           # e[j][r]
@@ -128,12 +151,11 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
         H = np.zeros((nt, 3, 3), dtype=dtype)
         lam = np.zeros((nt, 4, 4), dtype=dtype)
         rho = np.zeros((nt, 4), dtype=dtype)
-        valid = opp != 0xFFFF
         deg = valid.sum(axis=1)
         d_all = np.zeros((nt, 4, 3), dtype=dtype)
         for k in range(4):
             v = valid[:, k]
-            ok = np.where(v, opp[:, k], 0)
+            ok = opp[:, k]
             r = Xs[ok] - Xs[own[:, 0]]
             l123 = np.einsum("tjc,tc->tj", B, r)
             l0 = 1 - l123.sum(axis=1)
@@ -157,17 +179,20 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
                 col = np.where(valid[:, j], y[:, j, r], np.nan)
                 outb[(4 + j) * 3 + r, :nt] = col
         es_tot += es.sum(); eb_tot += eb.sum()
-        # phase 2: sliced-ELL gather
-        gp = plan["ell_grp_ptr"][td["grp_off"]: td["grp_off"] + td["ngrp"] + 1]
-        acc = np.zeros((td["ngrp"] * 32, 3), dtype=dtype)
-        for g in range(td["ngrp"]):
-            blk = plan["ell"][td["ell_off"] + gp[g]: td["ell_off"] + gp[g + 1]].reshape(-1, 32).astype(np.int64)
+        # phase 2: sliced-ELL gather (entries are word offsets into the [24][TT] table)
+        gp = td["grp_ptr"]
+        ngrp = int(td["ngrp"])
+        flat = outb.reshape(-1)
+        acc = np.zeros((ngrp * 32, 3), dtype=dtype)
+        ell = plan["ell"][td["ell_off"]: td["ell_off"] + td["nell"]]
+        for g in range(ngrp):
+            blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32).astype(np.int64)
             for lane in range(32):
                 ent = blk[:, lane]
                 ent = ent[ent != 0xFFFF]
                 for c in range(3):
-                    acc[g * 32 + lane, c] = outb[(ent & 7) * 3 + c, ent >> 3].sum()
-        dest = plan["dest"][vo:vo + nv]
+                    acc[g * 32 + lane, c] = flat[ent + c * TT].sum()
+        dest = td["dest"]
         for pidx in range(nv):
             dd = int(dest[pidx])
             if dd >= 0:
@@ -176,11 +201,17 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
             else:
                 assert np.isnan(scratch[-1 - dd, 0]), "scratch slot written twice"
                 scratch[-1 - dd] = acc[pidx]
-    # phase 3: combine shared vertices
+    # phase 3: combine shared vertices, group by group as the last-arriver CTAs do
+    cg = plan["cg"].reshape(-1, 4)
+    arrivals = np.zeros(plan["n_tiles"], dtype=np.int64)
+    for td in plan["tiles"]:
+        for owner, need, s0, s1 in cg[td["cg_off"]: td["cg_off"] + td["ncg"]]:
+            assert need == plan["need"][owner] and s0 == plan["gsv_ptr"][owner] and s1 == plan["gsv_ptr"][owner + 1]
+            arrivals[owner] += 1
+    assert np.array_equal(arrivals, plan["need"]), "arrival counters would not complete"
     for o in range(plan["n_tiles"]):
         for sv in range(plan["gsv_ptr"][o], plan["gsv_ptr"][o + 1]):
-            s0, s1 = plan["sv_slot_ptr"][sv], plan["sv_slot_ptr"][sv + 1]
-            vid = int(plan["sv_vid"][sv])
+            vid, s0, cnt, _ = sv_rec[sv]
             assert np.isnan(grad[vid, 0]), "shared vertex also written as exclusive"
-            grad[vid] = gradH * scratch[s0:s1].sum(axis=0)
+            grad[vid] = gradH * scratch[s0:s0 + cnt].sum(axis=0)
     return c1 * es_tot + c2 * eb_tot, es_tot, eb_tot, grad

@@ -31,6 +31,7 @@ class tsb_info_t(C.Structure):
         ("n_components", C.c_int32), ("n_shared_vertices", C.c_int32),
         ("n_local_vertices", C.c_int64), ("device_bytes", C.c_int64), ("stream_bytes", C.c_int64),
         ("n_boundary_faces", C.c_int32), ("max_local_vertices", C.c_int32),
+        ("fill", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -91,36 +91,36 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
   if (po.max_local_vertices == 0)
     return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets " + std::to_string(po.tile_tets) + " (compiled: 256, 512, 1024)");
+  po.ell_cap = tsb::ell_cap_for(po.tile_tets);
+
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(nullptr, TSB_E_CUDA, "cannot select CUDA device " + std::to_string(device));
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) po.balance_sms = sms;
+    if (const char *env = std::getenv("TSSPLAT_B200_BALANCE")) po.balance_sms = std::atoi(env) ? po.balance_sms : 0;
+  }
 
   tsb::HostPlan plan;
   std::string err;
   int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, plan, err);
   if (rc != TSB_OK) return fail(nullptr, rc, err);
 
-  DeviceGuard guard(device);
-  if (!guard.ok) return fail(nullptr, TSB_E_CUDA, "cannot select CUDA device " + std::to_string(device));
-  cudaError_t ce = tsb::prepare_energy_grad(po.tile_tets, po.max_local_vertices);
+  cudaError_t ce = tsb::prepare_energy_grad(po.tile_tets);
   if (ce != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(ce));
 
   tsb_handle_t h = new tsb_handle_s();
   h->device = device;
   tsb::KParams &kp = h->kp;
-  const uint16_t *idx16 = nullptr;
+  const int32_t *cg32 = nullptr, *sv32 = nullptr;
 #define TSB_TRY(expr) do { rc = (expr); if (rc != TSB_OK) { g_create_err = h->err; tsb_destroy(h); return rc; } } while (0)
-  TSB_TRY(upload(h, plan.tiles, &kp.tiles));
-  TSB_TRY(upload(h, plan.idx8, &idx16, 8));
-  kp.idx8 = reinterpret_cast<const uint4 *>(idx16);
-  TSB_TRY(upload(h, plan.Bsoa, &kp.Bsoa));
-  TSB_TRY(upload(h, plan.vlist, &kp.vlist));
-  TSB_TRY(upload(h, plan.Xloc, &kp.Xloc));
-  TSB_TRY(upload(h, plan.dest, &kp.dest));
-  TSB_TRY(upload(h, plan.ell, &kp.ell));
-  TSB_TRY(upload(h, plan.ell_grp_ptr, &kp.ell_grp_ptr));
-  TSB_TRY(upload(h, plan.cg_list, &kp.cg_list));
-  TSB_TRY(upload(h, plan.need, &kp.need));
-  TSB_TRY(upload(h, plan.gsv_ptr, &kp.gsv_ptr));
-  TSB_TRY(upload(h, plan.sv_vid, &kp.sv_vid));
-  TSB_TRY(upload(h, plan.sv_slot_ptr, &kp.sv_slot_ptr));
+  TSB_TRY(upload(h, plan.vblob, &kp.vblob, 16));
+  TSB_TRY(upload(h, plan.tblob, &kp.tblob, 16));
+  TSB_TRY(upload(h, plan.ell, &kp.ell, 8));
+  TSB_TRY(upload(h, plan.cg, &cg32, 4));
+  TSB_TRY(upload(h, plan.sv_rec, &sv32, 4));
+  kp.cg = reinterpret_cast<const int4 *>(cg32);
+  kp.sv_rec = reinterpret_cast<const int4 *>(sv32);
   TSB_TRY(alloc_zero(h, size_t(plan.n_tiles), &kp.done));
   TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 3, &kp.scratch));
   TSB_TRY(alloc_zero(h, size_t(plan.n_tiles) * 2, &kp.tile_energy));
@@ -128,17 +128,20 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
 #undef TSB_TRY
   kp.laplacian_scale = plan.laplacian_scale;
   kp.n_tiles = plan.n_tiles;
+  kp.fill = plan.fill;
 
   tsb_info_t &I = h->info;
   I.n = plan.n; I.nele = plan.nele; I.n_tiles = plan.n_tiles; I.tile_tets = plan.tile_tets;
   I.n_components = plan.n_components; I.n_shared_vertices = plan.n_shared_vertices;
   I.n_local_vertices = plan.n_local_vertices; I.n_boundary_faces = plan.n_boundary_faces;
   I.max_local_vertices = plan.max_local_vertices;
-  // bytes one launch moves through the memory system (useful tile payload, not padding):
-  //   per tet 16 (stencil ids) + 36 (rest inverse); per staged vertex 4 (id) + 12 (x) + 12 (X) + 4 (dest);
-  //   gather table 2 B/entry; grad 12 B/vertex; shared-vertex partials written + read
-  I.stream_bytes = int64_t(plan.nele) * 52 + plan.n_local_vertices * 32 + int64_t(plan.ell.size()) * 2 +
-                   int64_t(plan.n) * 12 + int64_t(plan.n_slots) * 24 + int64_t(plan.n_tiles) * (32 + 8);
+  I.fill = plan.fill;
+  // bytes one launch requests from the memory system: the fixed-size vertex-blob and tet-blob TMA
+  // copies, the gather tables, x gathered per staged vertex (12 B), grad (12 B/vertex), the
+  // shared-vertex partials written + read back, per-tile energies
+  I.stream_bytes = int64_t(plan.n_tiles) * (tsb::vblob_bytes(plan.max_local_vertices) + int64_t(52) * plan.fill) +
+                   int64_t(plan.ell.size()) * 2 + plan.n_local_vertices * 12 + int64_t(plan.n) * 12 +
+                   int64_t(plan.n_slots) * 24 + int64_t(plan.n_shared_vertices) * 16 + int64_t(plan.n_tiles) * 16;
   *out = h;
   return TSB_OK;
 }
@@ -169,7 +172,7 @@ int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int3
   tsb::KParams kp = h->kp;
   kp.x = x_dev; kp.grad = grad_out_dev; kp.energy_out = energy_out_dev; kp.gradH_dev = gradH_dev;
   kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
-  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, h->info.max_local_vertices, static_cast<cudaStream_t>(stream));
+  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
@@ -220,7 +223,7 @@ int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, fl
 struct tsb_debug_plan_s { tsb::HostPlan plan; };
 
 int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele, int32_t tile_tets,
-                         int32_t laplacian_scale, tsb_debug_plan_s **out) {
+                         int32_t laplacian_scale, int32_t balance_sms, tsb_debug_plan_s **out) {
   if (!out) return TSB_E_INVALID;
   *out = nullptr;
   tsb::PlanOptions po;
@@ -228,6 +231,8 @@ int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, 
   po.laplacian_scale = laplacian_scale;
   po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
   if (po.max_local_vertices == 0) return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets");
+  po.ell_cap = tsb::ell_cap_for(po.tile_tets);
+  po.balance_sms = balance_sms;
   tsb_debug_plan_s *d = new tsb_debug_plan_s();
   std::string err;
   const int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, d->plan, err);
@@ -242,19 +247,18 @@ int tsb_debug_plan_array(tsb_debug_plan_s *d, const char *name, const void **ptr
   const tsb::HostPlan &P = d->plan;
   const std::string k(name);
 #define TSB_ARR(nm, vec) if (k == nm) { *ptr = (vec).data(); *count = int64_t((vec).size()); *elem_bytes = int32_t(sizeof((vec)[0])); return TSB_OK; }
-  TSB_ARR("tiles", P.tiles) TSB_ARR("idx8", P.idx8) TSB_ARR("Bsoa", P.Bsoa) TSB_ARR("vlist", P.vlist)
-  TSB_ARR("Xloc", P.Xloc) TSB_ARR("dest", P.dest) TSB_ARR("ell", P.ell) TSB_ARR("ell_grp_ptr", P.ell_grp_ptr)
-  TSB_ARR("cg_list", P.cg_list) TSB_ARR("need", P.need) TSB_ARR("gsv_ptr", P.gsv_ptr) TSB_ARR("sv_vid", P.sv_vid)
-  TSB_ARR("sv_slot_ptr", P.sv_slot_ptr) TSB_ARR("tet_order", P.tet_order)
+  TSB_ARR("vblob", P.vblob) TSB_ARR("tblob", P.tblob) TSB_ARR("ell", P.ell) TSB_ARR("cg", P.cg)
+  TSB_ARR("sv_rec", P.sv_rec) TSB_ARR("need", P.need) TSB_ARR("gsv_ptr", P.gsv_ptr)
+  TSB_ARR("tet_order", P.tet_order) TSB_ARR("tile_first", P.tile_first)
 #undef TSB_ARR
   return TSB_E_INVALID;
 }
 
-int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {
+int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {  /* out8: 10 ints */
   if (!d || !out8) return TSB_E_INVALID;
   const tsb::HostPlan &P = d->plan;
   out8[0] = P.n; out8[1] = P.nele; out8[2] = P.tile_tets; out8[3] = P.max_local_vertices; out8[4] = P.n_tiles;
-  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots;
+  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots; out8[8] = P.fill; out8[9] = P.ell_cap;
   return TSB_OK;
 }
 

@@ -18,13 +18,15 @@
 // passes, no grid sync.  The barrier term is the reference's: max(-det F,0)^p, p in {2,4}
 // (cu:48-66), gradient -p(-J)^(p-1) cof(F) (cu:68-102).
 //
-// Execution.  One CTA per tile (<= TT tets, <= NVMAX staged vertices):
-//   phase 0  stage x (gathered through vlist) and rest X of the tile's vertices in shared memory
-//   phase 1  one tet per thread: gather 8 vertices from smem, energy terms, 8 output 3-vectors
+// Execution.  One CTA per tile (<= TT tets, <= NV staged vertices).  At kernel start one thread
+// issues TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the tile's vertex blob, tet blob
+// and gather table from global to shared memory; every later phase reads only shared memory.
+//   phase 0  gather x through the staged vertex list (the only indirection left in global memory)
+//   phase 1  one tet per thread, branch-free: 13 smem gathers, energy terms, 8 output 3-vectors
 //            written to a [24][TT] smem table (conflict-free stores)
 //   phase 2  one staged vertex per thread: sum its table entries through a 32-wide sliced-ELL
-//            list (coalesced u16 loads, deterministic order); vertices touched by this tile only
-//            are stored straight to grad, shared ones go to a per-(tile,vertex) scratch slot
+//            list (deterministic order); vertices touched by this tile only are stored straight to
+//            grad, shared ones go to a per-(tile,vertex) scratch slot
 //   phase 3  last-arriver combine: per owner tile an arrival counter; the CTA that completes a
 //            group sums its shared vertices' slots in fixed order -> deterministic, single launch.
 //            Same pattern folds the per-tile energies (fp64, fixed order) into energy_out.
@@ -51,51 +53,120 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <int TT, int NVMAX>
+// ---- mbarrier + TMA bulk copy (1-D) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <int TT, int NV, int ELLCAP>
 struct Smem {
-  static constexpr int kXs4Bytes = NVMAX * 16;
-  static constexpr int kXs2Bytes = NVMAX * 8;
-  static constexpr int kOutBytes = 24 * TT * 4;
-  static constexpr int kBytes = kXs4Bytes + kXs2Bytes + kOutBytes;
+  static constexpr int kVBytes = 64 + 20 * NV + 4 * (NV / 32 + 4);
+  static constexpr int kVOff = 0;
+  static constexpr int kTOff = align_up(kVOff + kVBytes, 128);
+  static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
+  static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
+  static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
+  static constexpr int kBytes = kOutOff + 96 * TT;
 };
 
-template <int TT, int NVMAX, int NT, bool WITH_GRAD>
-__global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__ KParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *xs4 = reinterpret_cast<float4 *>(smem_raw);                                  // x, y, z, X
-  float2 *xs2 = reinterpret_cast<float2 *>(smem_raw + Smem<TT, NVMAX>::kXs4Bytes);     // Y, Z
-  float *outb = reinterpret_cast<float *>(smem_raw + Smem<TT, NVMAX>::kXs4Bytes + Smem<TT, NVMAX>::kXs2Bytes);
+template <int TT, typename EllPtr>
+__device__ __forceinline__ void gather_vertex(const float *outb, EllPtr ep, int len, float &g0, float &g1, float &g2) {
+#pragma unroll 4
+  for (int k = 0; k < len; ++k) {
+    const unsigned en = ep[k * 32];
+    if (en != 0xffffu) {
+      const float *o = outb + en;
+      g0 += o[0]; g1 += o[TT]; g2 += o[2 * TT];
+    }
+  }
+}
+
+template <int TT, int NV, int ELLCAP, int NT, int MINB, bool WITH_GRAD>
+__global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_constant__ KParams p) {
+  using L = Smem<TT, NV, ELLCAP>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const TileHeader *hd = reinterpret_cast<const TileHeader *>(smem_raw + L::kVOff);
+  const int32_t *vlist_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64);
+  const float *Xx_s = reinterpret_cast<const float *>(smem_raw + L::kVOff + 64 + 4 * NV);
+  const float2 *xs2 = reinterpret_cast<const float2 *>(smem_raw + L::kVOff + 64 + 8 * NV);     // (Y, Z) rest
+  const int32_t *dest_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV);
+  const int32_t *grp_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 20 * NV);
+  const uint4 *idx_s = reinterpret_cast<const uint4 *>(smem_raw + L::kTOff);
+  const float *B_s = reinterpret_cast<const float *>(smem_raw + L::kTOff + 16 * TT);
+  const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(smem_raw + L::kEllOff);
+  float4 *xs4 = reinterpret_cast<float4 *>(smem_raw + L::kXs4Off);                               // x, y, z, X
+  float *outb = reinterpret_cast<float *>(smem_raw + L::kOutOff);
+  __shared__ __align__(8) uint64_t s_bar[3];
   __shared__ float s_red[2 * (NT / 32)];
+  __shared__ int4 s_cg[32];
   __shared__ int s_flag[33];
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
-  const TileDesc td = p.tiles[tile];
 
-  // ---------------- phase 0: stage vertices ---------------------------------------------------
-  for (int i = tid; i < td.nvert; i += NT) {
-    const int g = __ldg(p.vlist + td.vert_off + i);
-    const float *xp = p.x + 3 * size_t(g);
-    const float *Xp = p.Xloc + 3 * size_t(td.vert_off + i);
-    const float x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
-    const float X0 = __ldg(Xp), X1 = __ldg(Xp + 1), X2 = __ldg(Xp + 2);
-    xs4[i] = make_float4(x0, x1, x2, X0);
-    xs2[i] = make_float2(X1, X2);
+  // ---------------- stage the tile with TMA bulk copies ----------------------------------------
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&s_bar[0], L::kVBytes);
+    bulk_g2s(smem_raw + L::kVOff, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &s_bar[0]);
+    const uint32_t nt_b = uint32_t(p.fill);
+    mbar_expect_tx(&s_bar[1], 52u * nt_b);
+    const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
+    bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &s_bar[1]);
+    bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &s_bar[1]);
   }
   __syncthreads();
+  mbar_wait(&s_bar[0], 0);
+  const int ntet = hd->ntet, nvert = hd->nvert;
+  const int nell = hd->nell;
+  const bool ell_staged = nell <= ELLCAP;
+  if (WITH_GRAD && tid == 0 && ell_staged && nell > 0) {
+    mbar_expect_tx(&s_bar[2], 2u * uint32_t(nell));
+    bulk_g2s(smem_raw + L::kEllOff, p.ell + hd->ell_off, 2u * uint32_t(nell), &s_bar[2]);
+  }
+
+  // ---------------- phase 0: gather x --------------------------------------------------------------
+  for (int i = tid; i < nvert; i += NT) {
+    const float *xp = p.x + 3 * size_t(vlist_s[i]);
+    xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar[1], 0);
 
   // ---------------- phase 1: tets -----------------------------------------------------------------
   float es = 0.f, eb = 0.f;
   const float c1 = p.c1, c2 = p.c2;
   const int order = p.order;
-  for (int lt = tid; lt < td.ntet; lt += NT) {
-    const uint4 iv = __ldg(p.idx8 + size_t(tile) * TT + lt);
-    const float *Bp = p.Bsoa + size_t(tile) * 9 * TT + lt;
+  const bool lscale = p.laplacian_scale != 0;
+  for (int lt = tid; lt < ntet; lt += NT) {
+    const uint4 iv = idx_s[lt];
     float b[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) b[i] = __ldg(Bp + i * TT);
+    for (int i = 0; i < 9; ++i) b[i] = B_s[lt * 9 + i];
     const unsigned iown[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
-    const unsigned iopp[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
+    const unsigned ioppr[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
 
     const float4 p0 = xs4[iown[0]];
     const float2 q0 = xs2[iown[0]];
@@ -105,6 +176,11 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
       const float4 pj = xs4[iown[j + 1]];
       e[j][0] = pj.x - p0.x; e[j][1] = pj.y - p0.y; e[j][2] = pj.z - p0.z;
     }
+    float4 po[4];
+    float2 qo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { po[k] = xs4[ioppr[k] & 0x7fffu]; qo[k] = xs2[ioppr[k] & 0x7fffu]; }
+
     // hat gradients: a[0] = -(a1+a2+a3), a[j] = row j-1 of B
     float a[4][3];
 #pragma unroll
@@ -113,7 +189,9 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
       a[0][c] = -(b[c] + b[3 + c] + b[6 + c]);
     }
 
-    float z[4][3];  // gradient contributions to own vertices
+    float z[3][3];  // gradient contributions to own vertices 1..3 (vertex 0 follows from momentum)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
     {
       float F[3][3];
 #pragma unroll
@@ -121,17 +199,18 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 3; ++c) F[r][c] = e[0][r] * a[1][c] + e[1][r] * a[2][c] + e[2][r] * a[3][c];
       // cofactors = d det / dF  (tet_spheres_cuda.cu:32-46)
-      float C[3][3];
-      C[0][0] = F[1][1] * F[2][2] - F[1][2] * F[2][1];
-      C[0][1] = F[1][2] * F[2][0] - F[1][0] * F[2][2];
-      C[0][2] = F[1][0] * F[2][1] - F[1][1] * F[2][0];
-      const float J = F[0][0] * C[0][0] + F[0][1] * C[0][1] + F[0][2] * C[0][2];
-      if (J < 0.f) {
+      const float C00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
+      const float C01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
+      const float C02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
+      const float J = F[0][0] * C00 + F[0][1] * C01 + F[0][2] * C02;
+      if (J < 0.f) {   // rare: inverted tet
         const float m = -J;
         float coef;
         if (order == 2) { eb += m * m; coef = 2.f * m; }
         else { const float m2 = m * m; eb += m2 * m2; coef = 4.f * m2 * m; }
         if (WITH_GRAD) {
+          float C[3][3];
+          C[0][0] = C00; C[0][1] = C01; C[0][2] = C02;
           C[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
           C[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0];
           C[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
@@ -143,17 +222,14 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
           for (int r = 0; r < 3; ++r) {
             const float P0 = pc * C[r][0], P1 = pc * C[r][1], P2 = pc * C[r][2];
 #pragma unroll
-            for (int j = 1; j < 4; ++j) z[j][r] = P0 * a[j][0] + P1 * a[j][1] + P2 * a[j][2];
-            z[0][r] = -(z[1][r] + z[2][r] + z[3][r]);
+            for (int j = 0; j < 3; ++j) z[j][r] = P0 * a[j + 1][0] + P1 * a[j + 1][1] + P2 * a[j + 1][2];
           }
         }
-      } else if (WITH_GRAD) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
       }
     }
 
-    // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k
+    // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k      (branch-free; boundary faces have
+    // rho = 0 and gather the tet's own vertex)
     float H[3][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) { H[r][0] = 0.f; H[r][1] = 0.f; H[r][2] = 0.f; }
@@ -161,29 +237,24 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
     int deg = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      rho[k] = 0.f; lam[k][0] = 0.f; lam[k][1] = 0.f; lam[k][2] = 0.f;
-      if (iopp[k] != 0xffffu) {
-        ++deg;
-        const float4 po = xs4[iopp[k]];
-        const float2 qo = xs2[iopp[k]];
-        const float rx = po.w - p0.w, ry = qo.x - q0.x, rz = qo.y - q0.y;
-        const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
-        const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
-        const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
-        const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
-        const float rk = -1.f / lkk;
-        lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float xo = (r == 0) ? po.x : (r == 1 ? po.y : po.z);
-          const float x0 = (r == 0) ? p0.x : (r == 1 ? p0.y : p0.z);
-          const float d = (xo - x0) - l1 * e[0][r] - l2 * e[1][r] - l3 * e[2][r];
-          const float s = rk * d;
-          H[r][0] += s * a[k][0]; H[r][1] += s * a[k][1]; H[r][2] += s * a[k][2];
-        }
-      }
+      const bool valid = (ioppr[k] & 0x8000u) != 0u;
+      deg += valid ? 1 : 0;
+      const float rx = po[k].w - p0.w, ry = qo[k].x - q0.x, rz = qo[k].y - q0.y;
+      const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
+      const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
+      const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
+      const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
+      const float rk = valid ? __fdividef(-1.f, lkk) : 0.f;
+      lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
+      const float dx = (po[k].x - p0.x) - l1 * e[0][0] - l2 * e[1][0] - l3 * e[2][0];
+      const float dy = (po[k].y - p0.y) - l1 * e[0][1] - l2 * e[1][1] - l3 * e[2][1];
+      const float dz = (po[k].z - p0.z) - l1 * e[0][2] - l2 * e[1][2] - l3 * e[2][2];
+      const float sx = rk * dx, sy = rk * dy, sz = rk * dz;
+      H[0][0] += sx * a[k][0]; H[0][1] += sx * a[k][1]; H[0][2] += sx * a[k][2];
+      H[1][0] += sy * a[k][0]; H[1][1] += sy * a[k][1]; H[1][2] += sy * a[k][2];
+      H[2][0] += sz * a[k][0]; H[2][1] += sz * a[k][1]; H[2][2] += sz * a[k][2];
     }
-    const float w = (p.laplacian_scale && deg > 0) ? 1.f / float(deg) : 1.f;
+    const float w = (lscale && deg > 0) ? __fdividef(1.f, float(deg)) : 1.f;
     float hh = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -193,23 +264,25 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
 
     if (WITH_GRAD) {
       const float cw = c1 * w;
+      float ys[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (iopp[k] != 0xffffu) {
-          const float sk = cw * rho[k];
-          const float l0 = 1.f - lam[k][0] - lam[k][1] - lam[k][2];
+        const float sk = cw * rho[k];
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
-            outb[((4 + k) * 3 + r) * TT + lt] = y;
-            z[0][r] -= l0 * y; z[1][r] -= lam[k][0] * y; z[2][r] -= lam[k][1] * y; z[3][r] -= lam[k][2] * y;
-          }
+        for (int r = 0; r < 3; ++r) {
+          const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
+          outb[((4 + k) * 3 + r) * TT + lt] = y;
+          ys[r] += y;
+          z[0][r] -= lam[k][0] * y; z[1][r] -= lam[k][1] * y; z[2][r] -= lam[k][2] * y;
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) outb[(j * 3 + r) * TT + lt] = z[j][r];
+      for (int r = 0; r < 3; ++r) {
+        outb[(0 * 3 + r) * TT + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
+        outb[(1 * 3 + r) * TT + lt] = z[0][r];
+        outb[(2 * 3 + r) * TT + lt] = z[1][r];
+        outb[(3 * 3 + r) * TT + lt] = z[2][r];
+      }
     }
   }
 
@@ -229,22 +302,17 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
   if (WITH_GRAD) {
     if (p.gradH_dev) gh *= __ldg(p.gradH_dev);
     // ---------------- phase 2: per-vertex gather ------------------------------------------------
-    for (int pidx = tid; pidx < td.ngrp * 32; pidx += NT) {
+    if (ell_staged && nell > 0) mbar_wait(&s_bar[2], 0);
+    const int ngrp = hd->ngrp;
+    for (int pidx = tid; pidx < ngrp * 32; pidx += NT) {
       const int g = pidx >> 5, lane = pidx & 31;
-      const int beg = __ldg(p.ell_grp_ptr + td.grp_off + g), end = __ldg(p.ell_grp_ptr + td.grp_off + g + 1);
-      const uint16_t *ep = p.ell + size_t(td.ell_off) + beg + lane;
+      const int beg = grp_s[g], end = grp_s[g + 1];
       const int len = (end - beg) >> 5;
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < len; ++k) {
-        const unsigned en = __ldg(ep + k * 32);
-        if (en != 0xffffu) {
-          const float *o = outb + ((en & 7u) * 3) * TT + (en >> 3);
-          g0 += o[0]; g1 += o[TT]; g2 += o[2 * TT];
-        }
-      }
-      if (pidx < td.nvert) {
-        const int d = __ldg(p.dest + td.vert_off + pidx);
+      if (ell_staged) gather_vertex<TT>(outb, ell_s + beg + lane, len, g0, g1, g2);
+      else gather_vertex<TT>(outb, p.ell + size_t(hd->ell_off) + beg + lane, len, g0, g1, g2);
+      if (pidx < nvert) {
+        const int d = dest_s[pidx];
         if (d >= 0) {
           float *gp = p.grad + 3 * size_t(d);
           gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
@@ -259,14 +327,16 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
   // ---------------- phase 3: last-arriver combines ----------------------------------------------
   __threadfence();
   __syncthreads();
-  const int ncg = WITH_GRAD ? td.ncg : 0;
+  const int ncg = WITH_GRAD ? hd->ncg : 0;
+  const int cg_off = hd->cg_off;
   for (int base = 0; base < ncg + 1; base += 32) {   // slot `ncg` is the energy group
     if (tid < 32) {
       const int q = base + tid;
       int last = 0;
       if (q < ncg) {
-        const int o = __ldg(p.cg_list + td.cg_off + q);
-        last = (atomicAdd(p.done + o, 1) == __ldg(p.need + o) - 1);
+        const int4 c = __ldg(p.cg + cg_off + q);
+        s_cg[tid] = c;
+        last = (atomicAdd(p.done + c.x, 1) == c.y - 1);
       } else if (q == ncg) {
         last = (atomicAdd(p.energy_counter, 1u) == uint32_t(p.n_tiles - 1));
       }
@@ -278,19 +348,18 @@ __global__ void __launch_bounds__(NT) energy_grad_kernel(const __grid_constant__
       __threadfence();
       const int q = base + j;
       if (q < ncg) {
-        const int o = __ldg(p.cg_list + td.cg_off + q);
-        const int s0 = __ldg(p.gsv_ptr + o), s1 = __ldg(p.gsv_ptr + o + 1);
-        for (int sv = s0 + tid; sv < s1; sv += NT) {
-          const int a0 = __ldg(p.sv_slot_ptr + sv), a1 = __ldg(p.sv_slot_ptr + sv + 1);
+        const int4 c = s_cg[j];
+        for (int sv = c.z + tid; sv < c.w; sv += NT) {
+          const int4 rec = __ldg(p.sv_rec + sv);
           float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-          for (int s = a0; s < a1; ++s) {
+          for (int s = rec.y; s < rec.y + rec.z; ++s) {
             const float *sp = p.scratch + 3 * size_t(s);
             g0 += __ldcg(sp); g1 += __ldcg(sp + 1); g2 += __ldcg(sp + 2);
           }
-          float *gp = p.grad + 3 * size_t(__ldg(p.sv_vid + sv));
+          float *gp = p.grad + 3 * size_t(rec.x);
           gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
         }
-        if (tid == 0) p.done[o] = 0;
+        if (tid == 0) p.done[c.x] = 0;
       } else {
         // fold the per-tile energies in a fixed order, fp64
         double as = 0.0, ab = 0.0;
@@ -389,20 +458,25 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
   }
 }
 
-template <int TT, int NVMAX, int NT>
+// Compiled variants: tile capacity TT -> (staged vertices NV, gather-table entries ELLCAP, threads, min CTAs/SM)
+#define TSB_V256 256, 256, 256 * 14
+#define TSB_V512 512, 384, 512 * 11
+#define TSB_V1024 1024, 640, 1024 * 10
+
+template <int TT, int NV, int ELLCAP, int NT, int MINB>
 cudaError_t launch_variant(const KParams &p, cudaStream_t stream) {
-  const int smem = Smem<TT, NVMAX>::kBytes;
-  if (p.grad) energy_grad_kernel<TT, NVMAX, NT, true><<<p.n_tiles, NT, smem, stream>>>(p);
-  else energy_grad_kernel<TT, NVMAX, NT, false><<<p.n_tiles, NT, smem, stream>>>(p);
+  const int smem = Smem<TT, NV, ELLCAP>::kBytes;
+  if (p.grad) energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
+  else energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int TT, int NVMAX, int NT>
+template <int TT, int NV, int ELLCAP, int NT, int MINB>
 cudaError_t prepare_variant() {
-  const int smem = Smem<TT, NVMAX>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NVMAX, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = Smem<TT, NV, ELLCAP>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(energy_grad_kernel<TT, NVMAX, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return cudaFuncSetAttribute(energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 inline int grid_for(int64_t count, int block) {
@@ -412,40 +486,44 @@ inline int grid_for(int64_t count, int block) {
 
 }  // namespace
 
-// Compiled (tile_tets -> staged-vertex capacity) variants.
 int nvmax_for(int tile_tets) {
   switch (tile_tets) {
-    case 256: return 384;
-    case 512: return 640;
-    case 1024: return 1152;
+    case 256: return 256;
+    case 512: return 384;
+    case 1024: return 640;
   }
   return 0;
 }
 
-bool variant_supported(int tile_tets, int max_local_vertices) {
-  return nvmax_for(tile_tets) != 0 && max_local_vertices == nvmax_for(tile_tets);
+int ell_cap_for(int tile_tets) {
+  switch (tile_tets) {
+    case 256: return 256 * 14;
+    case 512: return 512 * 11;
+    case 1024: return 1024 * 10;
+  }
+  return 0;
 }
 
 static int g_threads_512 = 256;
 
-cudaError_t prepare_energy_grad(int tile_tets, int) {
+cudaError_t prepare_energy_grad(int tile_tets) {
   switch (tile_tets) {
-    case 256: return prepare_variant<256, 384, 256>();
+    case 256: return prepare_variant<TSB_V256, 256, 3>();
     case 512: {
-      cudaError_t e = prepare_variant<512, 640, 256>();
+      cudaError_t e = prepare_variant<TSB_V512, 256, 2>();
       if (e != cudaSuccess) return e;
-      return prepare_variant<512, 640, 512>();
+      return prepare_variant<TSB_V512, 512, 1>();
     }
-    case 1024: return prepare_variant<1024, 1152, 512>();
+    case 1024: return prepare_variant<TSB_V1024, 512, 1>();
   }
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int, cudaStream_t stream) {
+cudaError_t launch_energy_grad(const KParams &p, int tile_tets, cudaStream_t stream) {
   switch (tile_tets) {
-    case 256: return launch_variant<256, 384, 256>(p, stream);
-    case 512: return g_threads_512 == 512 ? launch_variant<512, 640, 512>(p, stream) : launch_variant<512, 640, 256>(p, stream);
-    case 1024: return launch_variant<1024, 1152, 512>(p, stream);
+    case 256: return launch_variant<TSB_V256, 256, 3>(p, stream);
+    case 512: return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, stream) : launch_variant<TSB_V512, 256, 2>(p, stream);
+    case 1024: return launch_variant<TSB_V1024, 512, 1>(p, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -10,19 +10,11 @@ namespace tsb {
 
 struct KParams {
   // plan (read-only, built once by tsb_create)
-  const TileDesc *tiles;
-  const uint4 *idx8;            // [n_tiles*tile_tets] 8 x u16 local vertex ids
-  const float *Bsoa;            // [n_tiles][9][tile_tets]
-  const int32_t *vlist;
-  const float *Xloc;
-  const int32_t *dest;
-  const uint16_t *ell;
-  const int32_t *ell_grp_ptr;
-  const int32_t *cg_list;
-  const int32_t *need;
-  const int32_t *gsv_ptr;
-  const int32_t *sv_vid;
-  const int32_t *sv_slot_ptr;
+  const unsigned char *vblob;   // n_tiles * vblob_bytes(NV)
+  const unsigned char *tblob;   // n_tiles * tblob_bytes(TT)
+  const uint16_t *ell;          // gather tables
+  const int4 *cg;               // (owner, need, sv_begin, sv_end) records
+  const int4 *sv_rec;           // (global vertex, first slot, slot count, 0) records
   // per-handle scratch
   int32_t *done;                // [n_tiles] arrival counters, self-resetting
   float *scratch;               // [3*n_slots] shared-vertex partials
@@ -37,14 +29,15 @@ struct KParams {
   int32_t order;                // 2 or 4
   int32_t laplacian_scale;
   int32_t n_tiles;
+  int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
 };
 
 // Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int max_local_vertices, cudaStream_t stream);
+cudaError_t launch_energy_grad(const KParams &p, int tile_tets, cudaStream_t stream);
 // One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
-cudaError_t prepare_energy_grad(int tile_tets, int max_local_vertices);
-bool variant_supported(int tile_tets, int max_local_vertices);
-int nvmax_for(int tile_tets);
+cudaError_t prepare_energy_grad(int tile_tets);
+int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
+int ell_cap_for(int tile_tets);   // gather-table entries the variant stages in shared memory
 void set_threads_512(int nt);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);

@@ -64,8 +64,8 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
                HostPlan &P, std::string &err) {
   if (!rest || !tets || n <= 0 || nele <= 0) { err = "null input or non-positive size"; return TSB_E_INVALID; }
   const int TT = opt.tile_tets, NVMAX = opt.max_local_vertices;
-  if (TT < 32 || TT > 4096 || (TT % 32) != 0 || NVMAX < 8 || NVMAX > 0xFFFE) {
-    err = "tile_tets must be a multiple of 32 in [32,4096]";
+  if (TT < 32 || TT > 2048 || (TT % 32) != 0 || NVMAX < 32 || NVMAX > 0x7FFF || (NVMAX % 32) != 0) {
+    err = "tile_tets must be a multiple of 32 in [32,2048]";
     return TSB_E_INVALID;
   }
   P = HostPlan();
@@ -160,49 +160,57 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   std::iota(P.tet_order.begin(), P.tet_order.end(), 0);
   std::stable_sort(P.tet_order.begin(), P.tet_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
 
-  // ---- greedy tiling: up to TT tets and NVMAX staged vertices per tile -----------------------------
-  std::vector<int32_t> tile_first;  // position in tet_order of each tile's first tet (+ sentinel)
+  // ---- tiling: `fill` tets per tile (wave-balanced), closed early if NVMAX vertices are reached ---
+  int fill = TT;
+  if (opt.balance_sms > 0) {
+    const int64_t per_round = int64_t(opt.balance_sms) * TT;
+    const int64_t rounds = (int64_t(nele) + per_round - 1) / per_round;
+    const int64_t tiles = rounds * opt.balance_sms;
+    fill = int((int64_t(nele) + tiles - 1) / tiles);
+    fill = std::min(TT, std::max(TT / 4, ((fill + 7) / 8) * 8));
+  }
+  P.fill = fill;
   {
     std::vector<int32_t> stamp(n, -1);
     int cur_tets = 0, cur_verts = 0, tile = 0;
-    tile_first.push_back(0);
+    P.tile_first.push_back(0);
     for (int pos = 0; pos < nele; ++pos) {
       const int t = P.tet_order[pos];
       int32_t st[8];
       for (int k = 0; k < 4; ++k) { st[k] = tets[4 * size_t(t) + k]; st[4 + k] = opp[4 * size_t(t) + k]; }
-      int add = 0;
-      for (int k = 0; k < 8; ++k) {
-        if (st[k] < 0 || stamp[st[k]] == tile) continue;
-        bool dup = false;
-        for (int j = 0; j < k; ++j) dup |= (st[j] == st[k]);
-        add += !dup;
-      }
-      if (cur_tets == TT || cur_verts + add > NVMAX) {
-        ++tile; tile_first.push_back(pos); cur_tets = 0; cur_verts = 0;
-        add = 0;
+      auto count_new = [&](int tl) {
+        int add = 0;
         for (int k = 0; k < 8; ++k) {
-          if (st[k] < 0) continue;
+          if (st[k] < 0 || stamp[st[k]] == tl) continue;
           bool dup = false;
           for (int j = 0; j < k; ++j) dup |= (st[j] == st[k]);
           add += !dup;
         }
+        return add;
+      };
+      int add = count_new(tile);
+      if (cur_tets == fill || cur_verts + add > NVMAX) {
+        ++tile; P.tile_first.push_back(pos); cur_tets = 0; cur_verts = 0;
+        add = count_new(tile);
       }
       for (int k = 0; k < 8; ++k) if (st[k] >= 0) stamp[st[k]] = tile;
       cur_tets += 1; cur_verts += add;
     }
-    tile_first.push_back(nele);
+    P.tile_first.push_back(nele);
   }
-  const int NTILE = int(tile_first.size()) - 1;
+  const int NTILE = int(P.tile_first.size()) - 1;
   P.n_tiles = NTILE;
-  P.tiles.resize(NTILE);
-  P.idx8.assign(size_t(NTILE) * TT * 8, 0xFFFF);
-  P.Bsoa.assign(size_t(NTILE) * 9 * TT, 0.f);
+  const int64_t VB = vblob_bytes(NVMAX), TB = tblob_bytes(TT);
+  P.vblob.assign(size_t(NTILE) * VB, 0);
+  P.tblob.assign(size_t(NTILE) * TB, 0);
+  P.ell_cap = opt.ell_cap > 0 ? opt.ell_cap : 8 * TT + 1024;
 
-  // ---- per tile: staged vertex list (id-sorted), local stencil ids ----------------------------
+  // ---- per tile: staged vertex list (id-sorted), local stencil ids, rest inverses ---------------
   std::vector<int32_t> local_of(n, -1);
   std::vector<std::vector<int32_t>> tile_verts(NTILE);
+  std::vector<uint16_t> idx8(size_t(NTILE) * TT * 8, 0);   // kept for the gather-table pass below
   for (int tile = 0; tile < NTILE; ++tile) {
-    const int p0 = tile_first[tile], p1 = tile_first[tile + 1];
+    const int p0 = P.tile_first[tile], p1 = P.tile_first[tile + 1];
     std::vector<int32_t> &vs = tile_verts[tile];
     vs.reserve(size_t(p1 - p0));
     for (int pos = p0; pos < p1; ++pos) {
@@ -215,23 +223,25 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     std::sort(vs.begin(), vs.end());
     vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
     for (size_t i = 0; i < vs.size(); ++i) local_of[vs[i]] = int32_t(i);
-    TileDesc &td = P.tiles[tile];
-    td.ntet = p1 - p0;
-    td.nvert = int32_t(vs.size());
-    td.vert_off = int32_t(P.n_local_vertices);
-    P.n_local_vertices += td.nvert;
+    P.n_local_vertices += int64_t(vs.size());
+    uint8_t *tb = P.tblob.data() + size_t(tile) * TB;
+    uint16_t *ids = reinterpret_cast<uint16_t *>(tb);
+    float *Bt = reinterpret_cast<float *>(tb + size_t(16) * TT);
     for (int pos = p0; pos < p1; ++pos) {
       const int t = P.tet_order[pos], lt = pos - p0;
-      uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+      uint16_t *d = ids + size_t(lt) * 8, *d2 = &idx8[(size_t(tile) * TT + lt) * 8];
       for (int k = 0; k < 4; ++k) {
         d[k] = uint16_t(local_of[tets[4 * size_t(t) + k]]);
         const int32_t o = opp[4 * size_t(t) + k];
-        d[4 + k] = o >= 0 ? uint16_t(local_of[o]) : uint16_t(0xFFFF);
+        // boundary face: point at the tet's own opposite vertex (harmless gather), bit 15 clear;
+        // interior face: neighbour's opposite vertex, bit 15 set
+        d[4 + k] = o >= 0 ? uint16_t(0x8000u | uint16_t(local_of[o])) : d[k];
+        d2[k] = d[k];
+        d2[4 + k] = o >= 0 ? uint16_t(local_of[o]) : uint16_t(0xFFFF);
       }
-      for (int i = 0; i < 9; ++i) P.Bsoa[(size_t(tile) * 9 + i) * TT + lt] = Binv[size_t(t) * 9 + i];
+      for (int i = 0; i < 9; ++i) Bt[size_t(lt) * 9 + i] = Binv[size_t(t) * 9 + i];
     }
   }
-  if (P.n_local_vertices > int64_t(0x7fffffff) - 64) { err = "mesh too large for 32-bit staging offsets"; return TSB_E_INVALID; }
 
   // ---- vertex -> touching tiles (ascending tile id), shared vertices, owners, scratch slots -----
   std::vector<int32_t> touch_ptr(size_t(n) + 1, 0);
@@ -250,37 +260,44 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     if (touch_ptr[size_t(v) + 1] - touch_ptr[v] > 1) shared.push_back(v);
   std::stable_sort(shared.begin(), shared.end(), [&](int32_t a, int32_t b) { return touch[touch_ptr[a]] < touch[touch_ptr[b]]; });
   P.n_shared_vertices = int32_t(shared.size());
-  P.sv_vid = shared;
-  P.sv_slot_ptr.assign(shared.size() + 1, 0);
+  P.sv_rec.assign(shared.size() * 4, 0);
   P.gsv_ptr.assign(size_t(NTILE) + 1, 0);
-  std::vector<int32_t> sv_of(n, -1);
+  std::vector<int32_t> sv_of(n, -1), slot0(shared.size() + 1, 0);
   for (size_t s = 0; s < shared.size(); ++s) {
     const int32_t v = shared[s];
     sv_of[v] = int32_t(s);
-    P.sv_slot_ptr[s + 1] = P.sv_slot_ptr[s] + (touch_ptr[size_t(v) + 1] - touch_ptr[v]);
+    const int cnt = touch_ptr[size_t(v) + 1] - touch_ptr[v];
+    slot0[s + 1] = slot0[s] + cnt;
+    P.sv_rec[4 * s] = v; P.sv_rec[4 * s + 1] = slot0[s]; P.sv_rec[4 * s + 2] = cnt;
     P.gsv_ptr[size_t(touch[touch_ptr[v]]) + 1]++;
   }
   for (int tile = 0; tile < NTILE; ++tile) P.gsv_ptr[size_t(tile) + 1] += P.gsv_ptr[tile];
-  P.n_slots = P.sv_slot_ptr[shared.size()];
+  P.n_slots = slot0[shared.size()];
 
-  // ---- per tile: staging arrays, gather table, contribution groups -----------------------------
-  P.vlist.resize(size_t(P.n_local_vertices));
-  P.Xloc.resize(size_t(P.n_local_vertices) * 3);
-  P.dest.resize(size_t(P.n_local_vertices));
+  // ---- per tile: vertex blob, gather table, contribution groups ---------------------------------
   P.need.assign(NTILE, 0);
-  std::vector<int32_t> deg, order_v, fill;
+  std::vector<int32_t> deg, order_v, fill_cnt, grp_rel;
+  std::vector<std::vector<int32_t>> tile_cg(NTILE);
   for (int tile = 0; tile < NTILE; ++tile) {
-    TileDesc &td = P.tiles[tile];
     const std::vector<int32_t> &vs = tile_verts[tile];
-    const int nv = td.nvert;
+    const int nv = int(vs.size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
+    uint8_t *vb = P.vblob.data() + size_t(tile) * VB;
+    TileHeader *hd = reinterpret_cast<TileHeader *>(vb);
+    int32_t *vlist = reinterpret_cast<int32_t *>(vb + 64);
+    float *Xx = reinterpret_cast<float *>(vb + 64 + size_t(4) * NVMAX);
+    float *YZ = reinterpret_cast<float *>(vb + 64 + size_t(8) * NVMAX);
+    int32_t *dest = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX);
+    int32_t *grp_ptr = reinterpret_cast<int32_t *>(vb + 64 + size_t(20) * NVMAX);
     for (int i = 0; i < nv; ++i) {
-      P.vlist[size_t(td.vert_off) + i] = vs[i];
-      for (int r = 0; r < 3; ++r) P.Xloc[3 * (size_t(td.vert_off) + i) + r] = rest[3 * size_t(vs[i]) + r];
+      vlist[i] = vs[i];
+      Xx[i] = rest[3 * size_t(vs[i])];
+      YZ[2 * i] = rest[3 * size_t(vs[i]) + 1];
+      YZ[2 * i + 1] = rest[3 * size_t(vs[i]) + 2];
     }
     // in-tile degree of each staged vertex (number of (tet, slot) entries that add into it)
     deg.assign(nv, 0);
-    for (int lt = 0; lt < td.ntet; ++lt) {
-      const uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+    for (int lt = 0; lt < ntet; ++lt) {
+      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
       for (int s = 0; s < 8; ++s) if (d[s] != 0xFFFF) deg[d[s]]++;
     }
     order_v.resize(nv);
@@ -288,45 +305,49 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     std::stable_sort(order_v.begin(), order_v.end(), [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
     std::vector<int32_t> slot_of_local(nv);  // local vertex -> position in the gather table
     for (int p = 0; p < nv; ++p) slot_of_local[order_v[p]] = p;
-    td.ngrp = (nv + 31) / 32;
-    td.grp_off = int32_t(P.ell_grp_ptr.size());
-    td.ell_off = int32_t(P.ell.size());
-    int32_t rel = 0;
-    for (int g = 0; g < td.ngrp; ++g) {
-      P.ell_grp_ptr.push_back(rel);
-      rel += 32 * deg[order_v[size_t(g) * 32]];  // group length = its first (largest) degree
-    }
-    P.ell_grp_ptr.push_back(rel);
-    if (size_t(td.ell_off) + size_t(rel) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
-    P.ell.resize(size_t(td.ell_off) + size_t(rel), 0xFFFF);
-    fill.assign(nv, 0);
-    for (int lt = 0; lt < td.ntet; ++lt) {
-      const uint16_t *d = &P.idx8[(size_t(tile) * TT + lt) * 8];
+    const int ngrp = (nv + 31) / 32;
+    grp_rel.assign(size_t(ngrp) + 1, 0);
+    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * deg[order_v[size_t(g) * 32]];  // group length = its largest degree
+    const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
+    while (P.ell.size() % 8) P.ell.push_back(0xFFFF);
+    if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
+    hd->ntet = ntet; hd->nvert = nv; hd->ngrp = ngrp; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
+    for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
+    P.ell.resize(size_t(hd->ell_off) + size_t(nell), 0xFFFF);
+    fill_cnt.assign(nv, 0);
+    for (int lt = 0; lt < ntet; ++lt) {
+      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
       for (int s = 0; s < 8; ++s) {
         if (d[s] == 0xFFFF) continue;
         const int p = slot_of_local[d[s]], g = p >> 5, lane = p & 31;
-        const size_t base = size_t(td.ell_off) + size_t(P.ell_grp_ptr[size_t(td.grp_off) + g]);
-        P.ell[base + size_t(fill[p]++) * 32 + lane] = uint16_t(lt * 8 + s);
+        const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
+        P.ell[base + size_t(fill_cnt[p]++) * 32 + lane] = uint16_t(s * 3 * TT + lt);  // word offset of component 0
       }
     }
     // destinations + owner groups
-    td.cg_off = int32_t(P.cg_list.size());
+    std::vector<int32_t> &cgl = tile_cg[tile];
     for (int p = 0; p < nv; ++p) {
       const int32_t v = vs[order_v[p]];
       const int32_t s = sv_of[v];
       if (s < 0) {
-        P.dest[size_t(td.vert_off) + p] = v;
+        dest[p] = v;
       } else {
         const int32_t *tb = &touch[touch_ptr[v]], *te = &touch[touch_ptr[size_t(v) + 1]];
         const int rank = int(std::lower_bound(tb, te, tile) - tb);
-        P.dest[size_t(td.vert_off) + p] = -1 - (P.sv_slot_ptr[s] + rank);
+        dest[p] = -1 - (slot0[s] + rank);
         const int32_t owner = tb[0];
-        bool seen = false;
-        for (size_t q = size_t(td.cg_off); q < P.cg_list.size(); ++q) seen |= (P.cg_list[q] == owner);
-        if (!seen) { P.cg_list.push_back(owner); P.need[owner]++; }
+        if (std::find(cgl.begin(), cgl.end(), owner) == cgl.end()) { cgl.push_back(owner); P.need[owner]++; }
       }
     }
-    td.ncg = int32_t(P.cg_list.size()) - td.cg_off;
+    hd->ncg = int32_t(cgl.size());
+  }
+  for (int tile = 0; tile < NTILE; ++tile) {
+    TileHeader *hd = reinterpret_cast<TileHeader *>(P.vblob.data() + size_t(tile) * VB);
+    hd->cg_off = int32_t(P.cg.size() / 4);
+    for (int32_t owner : tile_cg[tile]) {
+      P.cg.push_back(owner); P.cg.push_back(P.need[owner]);
+      P.cg.push_back(P.gsv_ptr[owner]); P.cg.push_back(P.gsv_ptr[size_t(owner) + 1]);
+    }
   }
   return TSB_OK;
 }
