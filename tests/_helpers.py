@@ -44,9 +44,9 @@ class COracle:
         return float(c1) * terms[0] + float(c2) * terms[1], terms, g
 
 
-_ARRAYS = {"vblob": np.uint8, "tblob": np.uint8, "ell": np.uint16, "cg": np.int32, "sv_rec": np.int32,
-           "need": np.int32, "gsv_ptr": np.int32, "tet_order": np.int32, "tile_first": np.int32}
-_HDR = ("ntet", "nvert", "ngrp", "ncg", "cg_off", "ell_off", "nell")
+_ARRAYS = {"vblob": np.uint8, "tblob": np.uint8, "ell": np.uint16, "slot_ptr": np.int32,
+           "tet_order": np.int32, "tile_first": np.int32}
+_HDR = ("ntet", "nvert", "ngrp", "ell_off", "nell")
 
 
 def vblob_bytes(nv):
@@ -95,14 +95,14 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0)
     for t in range(plan["n_tiles"]):
         vb = plan["vblob"][t * VB:(t + 1) * VB]
         tb = plan["tblob"][t * TB:(t + 1) * TB]
-        hdr = dict(zip(_HDR, vb[:28].view(np.int32)))
+        hdr = dict(zip(_HDR, vb[:20].view(np.int32)))
         nv, nt = int(hdr["nvert"]), int(hdr["ntet"])
         tiles.append(dict(
             hdr, vlist=vb[64:64 + 4 * NV].view(np.int32)[:nv],
             X=np.stack([vb[64 + 4 * NV:64 + 8 * NV].view(np.float32)[:nv],
                         vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 0],
                         vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 1]], axis=1),
-            dest=vb[64 + 16 * NV:64 + 20 * NV].view(np.int32)[:nv],
+            slot=vb[64 + 16 * NV:64 + 20 * NV].view(np.int32)[:nv],
             grp_ptr=vb[64 + 20 * NV:].view(np.int32)[:int(hdr["ngrp"]) + 1],
             idx8=tb[:16 * TT].view(np.uint16).reshape(-1, 8)[:nt],
             B=tb[16 * TT:].view(np.float32).reshape(-1, 9)[:nt]))
@@ -111,15 +111,15 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0)
 
 
 def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
-    """numpy re-enactment of tsb_kernels.cu's four phases on the host plan (same formulas, same data
-    structures, tile by tile).  Returns (energy_total, smooth, barrier, grad[n,3])."""
+    """numpy re-enactment of tsb_kernels.cu (tile kernel phases 0-2 + combine kernel) on the host
+    plan: same formulas, same data structures, tile by tile.
+    Returns (energy_total, smooth, barrier, grad[n,3])."""
     TT = plan["tile_tets"]
+    TTP = TT + 4
     x = np.asarray(x, dtype=np.float32).reshape(-1, 3).astype(dtype)
     n = plan["n"]
-    grad = np.full((n, 3), np.nan, dtype=dtype)
     scratch = np.full((max(plan["n_slots"], 1), 3), np.nan, dtype=dtype)
     es_tot = eb_tot = 0.0
-    sv_rec = plan["sv_rec"].reshape(-1, 4)
     for ti, td in enumerate(plan["tiles"]):
         nt, nv = int(td["ntet"]), int(td["nvert"])
         vl = td["vlist"]
@@ -172,46 +172,35 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
         y = (c1 * w)[:, None, None] * rho[:, :, None] * np.einsum("trc,tkc->tkr", H, a)   # nt x 4 x 3
         y = np.where(valid[:, :, None], y, 0)
         z = z - np.einsum("tkj,tkr->tjr", lam, y)
-        outb = np.full((24, TT), np.nan, dtype=dtype)           # phase 1 table
+        outb = np.full((24, TTP), np.nan, dtype=dtype)          # phase 1 table
+        outb[0:3, TT] = 0.0                                     # zero column
         for j in range(4):
             for r in range(3):
                 outb[j * 3 + r, :nt] = z[:, j, r]
-                col = np.where(valid[:, j], y[:, j, r], np.nan)
-                outb[(4 + j) * 3 + r, :nt] = col
+                outb[(4 + j) * 3 + r, :nt] = y[:, j, r]
         es_tot += es.sum(); eb_tot += eb.sum()
-        # phase 2: sliced-ELL gather (entries are word offsets into the [24][TT] table)
+        # phase 2: sliced-ELL gather (entries are word offsets into the [24][TT+4] table, stored as
+        # [k/2][lane][2] pairs; padding points at the zero column)
         gp = td["grp_ptr"]
         ngrp = int(td["ngrp"])
         flat = outb.reshape(-1)
         acc = np.zeros((ngrp * 32, 3), dtype=dtype)
         ell = plan["ell"][td["ell_off"]: td["ell_off"] + td["nell"]]
+        n_real = 0
         for g in range(ngrp):
-            blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32).astype(np.int64)
+            blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32, 2).astype(np.int64)
             for lane in range(32):
-                ent = blk[:, lane]
-                ent = ent[ent != 0xFFFF]
+                ent = blk[:, lane, :].reshape(-1)
+                n_real += int((ent != TT).sum())
                 for c in range(3):
-                    acc[g * 32 + lane, c] = flat[ent + c * TT].sum()
-        dest = td["dest"]
+                    acc[g * 32 + lane, c] = flat[ent + c * TTP].sum()
+        assert n_real == int(4 * nt + valid.sum()), "gather table must list every (tet, slot) exactly once"
         for pidx in range(nv):
-            dd = int(dest[pidx])
-            if dd >= 0:
-                assert np.isnan(grad[dd, 0]), "exclusive vertex written twice"
-                grad[dd] = gradH * acc[pidx]
-            else:
-                assert np.isnan(scratch[-1 - dd, 0]), "scratch slot written twice"
-                scratch[-1 - dd] = acc[pidx]
-    # phase 3: combine shared vertices, group by group as the last-arriver CTAs do
-    cg = plan["cg"].reshape(-1, 4)
-    arrivals = np.zeros(plan["n_tiles"], dtype=np.int64)
-    for td in plan["tiles"]:
-        for owner, need, s0, s1 in cg[td["cg_off"]: td["cg_off"] + td["ncg"]]:
-            assert need == plan["need"][owner] and s0 == plan["gsv_ptr"][owner] and s1 == plan["gsv_ptr"][owner + 1]
-            arrivals[owner] += 1
-    assert np.array_equal(arrivals, plan["need"]), "arrival counters would not complete"
-    for o in range(plan["n_tiles"]):
-        for sv in range(plan["gsv_ptr"][o], plan["gsv_ptr"][o + 1]):
-            vid, s0, cnt, _ = sv_rec[sv]
-            assert np.isnan(grad[vid, 0]), "shared vertex also written as exclusive"
-            grad[vid] = gradH * scratch[s0:s0 + cnt].sum(axis=0)
+            sl = int(td["slot"][pidx])
+            assert np.isnan(scratch[sl, 0]), "scratch slot written twice"
+            scratch[sl] = acc[pidx]
+    # combine kernel
+    sp = plan["slot_ptr"]
+    assert sp[0] == 0 and sp[-1] == plan["n_slots"] and not np.isnan(scratch[:plan["n_slots"]]).any()
+    grad = np.stack([gradH * scratch[sp[v]:sp[v + 1]].sum(axis=0) for v in range(n)])
     return c1 * es_tot + c2 * eb_tot, es_tot, eb_tot, grad

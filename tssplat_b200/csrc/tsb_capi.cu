@@ -16,6 +16,7 @@
 struct tsb_handle_s {
   int device = 0;
   tsb::KParams kp{};
+  const int32_t *slot_ptr = nullptr;
   tsb_info_t info{};
   std::vector<void *> allocs;
   std::string err;
@@ -112,19 +113,13 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   tsb_handle_t h = new tsb_handle_s();
   h->device = device;
   tsb::KParams &kp = h->kp;
-  const int32_t *cg32 = nullptr, *sv32 = nullptr;
 #define TSB_TRY(expr) do { rc = (expr); if (rc != TSB_OK) { g_create_err = h->err; tsb_destroy(h); return rc; } } while (0)
   TSB_TRY(upload(h, plan.vblob, &kp.vblob, 16));
   TSB_TRY(upload(h, plan.tblob, &kp.tblob, 16));
   TSB_TRY(upload(h, plan.ell, &kp.ell, 8));
-  TSB_TRY(upload(h, plan.cg, &cg32, 4));
-  TSB_TRY(upload(h, plan.sv_rec, &sv32, 4));
-  kp.cg = reinterpret_cast<const int4 *>(cg32);
-  kp.sv_rec = reinterpret_cast<const int4 *>(sv32);
-  TSB_TRY(alloc_zero(h, size_t(plan.n_tiles), &kp.done));
-  TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 3, &kp.scratch));
+  TSB_TRY(upload(h, plan.slot_ptr, &h->slot_ptr, 2));
+  TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 4, &kp.scratch));
   TSB_TRY(alloc_zero(h, size_t(plan.n_tiles) * 2, &kp.tile_energy));
-  TSB_TRY(alloc_zero(h, 1, &kp.energy_counter));
 #undef TSB_TRY
   kp.laplacian_scale = plan.laplacian_scale;
   kp.n_tiles = plan.n_tiles;
@@ -140,8 +135,8 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   // copies, the gather tables, x gathered per staged vertex (12 B), grad (12 B/vertex), the
   // shared-vertex partials written + read back, per-tile energies
   I.stream_bytes = int64_t(plan.n_tiles) * (tsb::vblob_bytes(plan.max_local_vertices) + int64_t(52) * plan.fill) +
-                   int64_t(plan.ell.size()) * 2 + plan.n_local_vertices * 12 + int64_t(plan.n) * 12 +
-                   int64_t(plan.n_slots) * 24 + int64_t(plan.n_shared_vertices) * 16 + int64_t(plan.n_tiles) * 16;
+                   int64_t(plan.ell.size()) * 2 + plan.n_local_vertices * 12 + int64_t(plan.n) * (12 + 4) +
+                   int64_t(plan.n_slots) * 32 + int64_t(plan.n_tiles) * 16;
   *out = h;
   return TSB_OK;
 }
@@ -172,7 +167,7 @@ int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int3
   tsb::KParams kp = h->kp;
   kp.x = x_dev; kp.grad = grad_out_dev; kp.energy_out = energy_out_dev; kp.gradH_dev = gradH_dev;
   kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
-  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, static_cast<cudaStream_t>(stream));
+  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, h->info.n, h->slot_ptr, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
@@ -247,8 +242,7 @@ int tsb_debug_plan_array(tsb_debug_plan_s *d, const char *name, const void **ptr
   const tsb::HostPlan &P = d->plan;
   const std::string k(name);
 #define TSB_ARR(nm, vec) if (k == nm) { *ptr = (vec).data(); *count = int64_t((vec).size()); *elem_bytes = int32_t(sizeof((vec)[0])); return TSB_OK; }
-  TSB_ARR("vblob", P.vblob) TSB_ARR("tblob", P.tblob) TSB_ARR("ell", P.ell) TSB_ARR("cg", P.cg)
-  TSB_ARR("sv_rec", P.sv_rec) TSB_ARR("need", P.need) TSB_ARR("gsv_ptr", P.gsv_ptr)
+  TSB_ARR("vblob", P.vblob) TSB_ARR("tblob", P.tblob) TSB_ARR("ell", P.ell) TSB_ARR("slot_ptr", P.slot_ptr)
   TSB_ARR("tet_order", P.tet_order) TSB_ARR("tile_first", P.tile_first)
 #undef TSB_ARR
   return TSB_E_INVALID;

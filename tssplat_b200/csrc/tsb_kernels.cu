@@ -25,12 +25,13 @@
 //   phase 1  one tet per thread, branch-free: 13 smem gathers, energy terms, 8 output 3-vectors
 //            written to a [24][TT] smem table (conflict-free stores)
 //   phase 2  one staged vertex per thread: sum its table entries through a 32-wide sliced-ELL
-//            list (deterministic order); vertices touched by this tile only are stored straight to
-//            grad, shared ones go to a per-(tile,vertex) scratch slot
-//   phase 3  last-arriver combine: per owner tile an arrival counter; the CTA that completes a
-//            group sums its shared vertices' slots in fixed order -> deterministic, single launch.
-//            Same pattern folds the per-tile energies (fp64, fixed order) into energy_out.
-// No global atomics on data, only on the arrival counters.
+//            list (deterministic order) and store the tile's partial gradient of that vertex to
+//            its own float4 scratch slot
+// A second, tiny kernel chained with programmatic dependent launch (griddepcontrol) sums each
+// vertex's slots in fixed order into grad (scaled by gradH) and folds the per-tile energies in
+// fp64.  No atomics, no fences, no grid sync: bitwise deterministic.  (Round-1 profile
+// profiles/r01_v2_single_launch.md: doing that combine inside the first kernel with a
+// last-arriver scheme cost 47% of warp time in fences, atomics and CTA barriers.)
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -87,18 +88,20 @@ struct Smem {
   static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
   static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
   static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
-  static constexpr int kBytes = kOutOff + 96 * TT;
+  static constexpr int kTTP = TT + 4;                 // output-table row stride; column TT holds zeros
+  static constexpr int kBytes = kOutOff + 96 * kTTP;
 };
 
-template <int TT, typename EllPtr>
-__device__ __forceinline__ void gather_vertex(const float *outb, EllPtr ep, int len, float &g0, float &g1, float &g2) {
+// Sum one vertex's table entries.  ep points at this lane's first (entry0, entry1) pair; pairs of
+// successive k are 32 words apart.  Padding entries point at the table's zero column.
+template <int TTP>
+__device__ __forceinline__ void gather_vertex(const float *outb, const uint32_t *ep, int len2, float &g0, float &g1, float &g2) {
 #pragma unroll 4
-  for (int k = 0; k < len; ++k) {
-    const unsigned en = ep[k * 32];
-    if (en != 0xffffu) {
-      const float *o = outb + en;
-      g0 += o[0]; g1 += o[TT]; g2 += o[2 * TT];
-    }
+  for (int k = 0; k < len2; ++k) {
+    const uint32_t pr = ep[k * 32];
+    const float *o0 = outb + (pr & 0xffffu), *o1 = outb + (pr >> 16);
+    g0 += o0[0]; g1 += o0[TTP]; g2 += o0[2 * TTP];
+    g0 += o1[0]; g1 += o1[TTP]; g2 += o1[2 * TTP];
   }
 }
 
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   const int32_t *vlist_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64);
   const float *Xx_s = reinterpret_cast<const float *>(smem_raw + L::kVOff + 64 + 4 * NV);
   const float2 *xs2 = reinterpret_cast<const float2 *>(smem_raw + L::kVOff + 64 + 8 * NV);     // (Y, Z) rest
-  const int32_t *dest_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV);
+  const int32_t *slot_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV);
   const int32_t *grp_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 20 * NV);
   const uint4 *idx_s = reinterpret_cast<const uint4 *>(smem_raw + L::kTOff);
   const float *B_s = reinterpret_cast<const float *>(smem_raw + L::kTOff + 16 * TT);
@@ -119,8 +122,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   float *outb = reinterpret_cast<float *>(smem_raw + L::kOutOff);
   __shared__ __align__(8) uint64_t s_bar[3];
   __shared__ float s_red[2 * (NT / 32)];
-  __shared__ int4 s_cg[32];
-  __shared__ int s_flag[33];
+  constexpr int TTP = L::kTTP;
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   }
 
   // ---------------- phase 0: gather x --------------------------------------------------------------
+  if (WITH_GRAD && tid < 3) outb[tid * TTP + TT] = 0.f;   // zero column for gather-table padding
   for (int i = tid; i < nvert; i += NT) {
     const float *xp = p.x + 3 * size_t(vlist_s[i]);
     xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
@@ -271,17 +274,17 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
-          outb[((4 + k) * 3 + r) * TT + lt] = y;
+          outb[((4 + k) * 3 + r) * TTP + lt] = y;
           ys[r] += y;
           z[0][r] -= lam[k][0] * y; z[1][r] -= lam[k][1] * y; z[2][r] -= lam[k][2] * y;
         }
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        outb[(0 * 3 + r) * TT + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
-        outb[(1 * 3 + r) * TT + lt] = z[0][r];
-        outb[(2 * 3 + r) * TT + lt] = z[1][r];
-        outb[(3 * 3 + r) * TT + lt] = z[2][r];
+        outb[(0 * 3 + r) * TTP + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
+        outb[(1 * 3 + r) * TTP + lt] = z[0][r];
+        outb[(2 * 3 + r) * TTP + lt] = z[1][r];
+        outb[(3 * 3 + r) * TTP + lt] = z[2][r];
       }
     }
   }
@@ -298,87 +301,62 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     if (tid == 0) { p.tile_energy[2 * tile] = vs; p.tile_energy[2 * tile + 1] = vb; }
   }
 
-  float gh = p.gradH;
+  // let the combine kernel's CTAs start launching while this tile finishes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (WITH_GRAD) {
-    if (p.gradH_dev) gh *= __ldg(p.gradH_dev);
     // ---------------- phase 2: per-vertex gather ------------------------------------------------
     if (ell_staged && nell > 0) mbar_wait(&s_bar[2], 0);
     const int ngrp = hd->ngrp;
+    float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
     for (int pidx = tid; pidx < ngrp * 32; pidx += NT) {
       const int g = pidx >> 5, lane = pidx & 31;
       const int beg = grp_s[g], end = grp_s[g + 1];
-      const int len = (end - beg) >> 5;
+      const int len2 = (end - beg) >> 6;
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (ell_staged) gather_vertex<TT>(outb, ell_s + beg + lane, len, g0, g1, g2);
-      else gather_vertex<TT>(outb, p.ell + size_t(hd->ell_off) + beg + lane, len, g0, g1, g2);
-      if (pidx < nvert) {
-        const int d = dest_s[pidx];
-        if (d >= 0) {
-          float *gp = p.grad + 3 * size_t(d);
-          gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
-        } else {
-          float *sp = p.scratch + 3 * size_t(-1 - d);
-          sp[0] = g0; sp[1] = g1; sp[2] = g2;
-        }
-      }
+      if (ell_staged) gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, len2, g0, g1, g2);
+      else gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(p.ell + size_t(hd->ell_off) + beg) + lane, len2, g0, g1, g2);
+      if (pidx < nvert) scratch4[slot_s[pidx]] = make_float4(g0, g1, g2, 0.f);
     }
   }
+}
 
-  // ---------------- phase 3: last-arriver combines ----------------------------------------------
-  __threadfence();
-  __syncthreads();
-  const int ncg = WITH_GRAD ? hd->ncg : 0;
-  const int cg_off = hd->cg_off;
-  for (int base = 0; base < ncg + 1; base += 32) {   // slot `ncg` is the energy group
-    if (tid < 32) {
-      const int q = base + tid;
-      int last = 0;
-      if (q < ncg) {
-        const int4 c = __ldg(p.cg + cg_off + q);
-        s_cg[tid] = c;
-        last = (atomicAdd(p.done + c.x, 1) == c.y - 1);
-      } else if (q == ncg) {
-        last = (atomicAdd(p.energy_counter, 1u) == uint32_t(p.n_tiles - 1));
-      }
-      s_flag[tid] = last;
+// Combine kernel: grad[v] = gradH * sum of v's scratch slots (fixed order); block 0 also folds the
+// per-tile energies in fp64.  Launched with programmatic stream serialization right behind the
+// tile kernel; griddepcontrol.wait blocks until that grid has completed and flushed.
+template <int NT>
+__global__ void __launch_bounds__(NT) combine_kernel(const __grid_constant__ KParams p, int n_vertices, const int32_t *__restrict__ slot_ptr) {
+  const int tid = threadIdx.x;
+  const int v = blockIdx.x * NT + tid;
+  int s0 = 0, s1 = 0;
+  if (v < n_vertices) { s0 = __ldg(slot_ptr + v); s1 = __ldg(slot_ptr + v + 1); }   // plan data: safe before the wait
+  float gh = p.gradH;
+  if (p.gradH_dev) gh *= __ldg(p.gradH_dev);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (v < n_vertices) {
+    const float4 *scratch4 = reinterpret_cast<const float4 *>(p.scratch);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    for (int s = s0; s < s1; ++s) {
+      const float4 q = __ldcg(scratch4 + s);
+      g0 += q.x; g1 += q.y; g2 += q.z;
     }
+    float *gp = p.grad + 3 * size_t(v);
+    gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
+  }
+  if (blockIdx.x == 0) {
+    double as = 0.0, ab = 0.0;
+    for (int t = tid; t < p.n_tiles; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
+    as = warp_sum(as); ab = warp_sum(ab);
+    __shared__ double s_dred[2 * (NT / 32)];
+    if ((tid & 31) == 0) { s_dred[tid >> 5] = as; s_dred[NT / 32 + (tid >> 5)] = ab; }
     __syncthreads();
-    for (int j = 0; j < 32 && base + j <= ncg; ++j) {
-      if (!s_flag[j]) continue;
-      __threadfence();
-      const int q = base + j;
-      if (q < ncg) {
-        const int4 c = s_cg[j];
-        for (int sv = c.z + tid; sv < c.w; sv += NT) {
-          const int4 rec = __ldg(p.sv_rec + sv);
-          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-          for (int s = rec.y; s < rec.y + rec.z; ++s) {
-            const float *sp = p.scratch + 3 * size_t(s);
-            g0 += __ldcg(sp); g1 += __ldcg(sp + 1); g2 += __ldcg(sp + 2);
-          }
-          float *gp = p.grad + 3 * size_t(rec.x);
-          gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
-        }
-        if (tid == 0) p.done[c.x] = 0;
-      } else {
-        // fold the per-tile energies in a fixed order, fp64
-        double as = 0.0, ab = 0.0;
-        for (int t = tid; t < p.n_tiles; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
-        as = warp_sum(as); ab = warp_sum(ab);
-        __shared__ double s_dred[2 * (NT / 32)];
-        if ((tid & 31) == 0) { s_dred[tid >> 5] = as; s_dred[NT / 32 + (tid >> 5)] = ab; }
-        __syncthreads();
-        if (tid == 0) {
-          double ts = 0.0, tb = 0.0;
-          for (int wgt = 0; wgt < NT / 32; ++wgt) { ts += s_dred[wgt]; tb += s_dred[NT / 32 + wgt]; }
-          p.energy_out[0] = float(double(p.c1) * ts + double(p.c2) * tb);
-          p.energy_out[1] = float(ts);
-          p.energy_out[2] = float(tb);
-          *p.energy_counter = 0u;
-        }
-      }
+    if (tid == 0) {
+      double ts = 0.0, tb = 0.0;
+      for (int wgt = 0; wgt < NT / 32; ++wgt) { ts += s_dred[wgt]; tb += s_dred[NT / 32 + wgt]; }
+      p.energy_out[0] = float(double(p.c1) * ts + double(p.c2) * tb);
+      p.energy_out[1] = float(ts);
+      p.energy_out[2] = float(tb);
     }
-    __syncthreads();
   }
 }
 
@@ -464,11 +442,26 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
 #define TSB_V1024 1024, 640, 1024 * 10
 
 template <int TT, int NV, int ELLCAP, int NT, int MINB>
-cudaError_t launch_variant(const KParams &p, cudaStream_t stream) {
+cudaError_t launch_variant(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   const int smem = Smem<TT, NV, ELLCAP>::kBytes;
   if (p.grad) energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
   else energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // combine kernel, chained with programmatic dependent launch
+  constexpr int CNT = 256;
+  const int nv = p.grad ? n_vertices : 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(nv > 0 ? (nv + CNT - 1) / CNT : 1));
+  cfg.blockDim = dim3(CNT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, combine_kernel<CNT>, p, nv, slot_ptr);
 }
 
 template <int TT, int NV, int ELLCAP, int NT, int MINB>
@@ -519,11 +512,11 @@ cudaError_t prepare_energy_grad(int tile_tets) {
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, cudaStream_t stream) {
+cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   switch (tile_tets) {
-    case 256: return launch_variant<TSB_V256, 256, 3>(p, stream);
-    case 512: return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, stream) : launch_variant<TSB_V512, 256, 2>(p, stream);
-    case 1024: return launch_variant<TSB_V1024, 512, 1>(p, stream);
+    case 256: return launch_variant<TSB_V256, 256, 3>(p, n_vertices, slot_ptr, stream);
+    case 512: return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, n_vertices, slot_ptr, stream) : launch_variant<TSB_V512, 256, 2>(p, n_vertices, slot_ptr, stream);
+    case 1024: return launch_variant<TSB_V1024, 512, 1>(p, n_vertices, slot_ptr, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -13,13 +13,9 @@ struct KParams {
   const unsigned char *vblob;   // n_tiles * vblob_bytes(NV)
   const unsigned char *tblob;   // n_tiles * tblob_bytes(TT)
   const uint16_t *ell;          // gather tables
-  const int4 *cg;               // (owner, need, sv_begin, sv_end) records
-  const int4 *sv_rec;           // (global vertex, first slot, slot count, 0) records
   // per-handle scratch
-  int32_t *done;                // [n_tiles] arrival counters, self-resetting
-  float *scratch;               // [3*n_slots] shared-vertex partials
+  float *scratch;               // [4*n_slots] per-(tile,vertex) partial gradients (float4)
   float *tile_energy;           // [2*n_tiles] (smooth, barrier) per tile
-  uint32_t *energy_counter;     // self-resetting
   // per launch
   const float *x;               // [3n]
   float *grad;                  // [3n] or nullptr (energy only)
@@ -33,7 +29,7 @@ struct KParams {
 };
 
 // Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, cudaStream_t stream);
+cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
 // One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
 cudaError_t prepare_energy_grad(int tile_tets);
 int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)

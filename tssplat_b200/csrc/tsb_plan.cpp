@@ -254,30 +254,14 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     for (int tile = 0; tile < NTILE; ++tile)
       for (int32_t v : tile_verts[tile]) touch[size_t(cur[v]++)] = tile;
   }
-  // shared vertices ordered by (owner tile, vertex id); owner = lowest touching tile
-  std::vector<int32_t> shared;
-  for (int v = 0; v < n; ++v)
-    if (touch_ptr[size_t(v) + 1] - touch_ptr[v] > 1) shared.push_back(v);
-  std::stable_sort(shared.begin(), shared.end(), [&](int32_t a, int32_t b) { return touch[touch_ptr[a]] < touch[touch_ptr[b]]; });
-  P.n_shared_vertices = int32_t(shared.size());
-  P.sv_rec.assign(shared.size() * 4, 0);
-  P.gsv_ptr.assign(size_t(NTILE) + 1, 0);
-  std::vector<int32_t> sv_of(n, -1), slot0(shared.size() + 1, 0);
-  for (size_t s = 0; s < shared.size(); ++s) {
-    const int32_t v = shared[s];
-    sv_of[v] = int32_t(s);
-    const int cnt = touch_ptr[size_t(v) + 1] - touch_ptr[v];
-    slot0[s + 1] = slot0[s] + cnt;
-    P.sv_rec[4 * s] = v; P.sv_rec[4 * s + 1] = slot0[s]; P.sv_rec[4 * s + 2] = cnt;
-    P.gsv_ptr[size_t(touch[touch_ptr[v]]) + 1]++;
-  }
-  for (int tile = 0; tile < NTILE; ++tile) P.gsv_ptr[size_t(tile) + 1] += P.gsv_ptr[tile];
-  P.n_slots = slot0[shared.size()];
+  // scratch slots: one per (vertex, touching tile), contiguous per vertex
+  P.slot_ptr.assign(touch_ptr.begin(), touch_ptr.end());
+  P.n_slots = touch_ptr[n];
+  for (int v = 0; v < n; ++v) P.n_shared_vertices += (touch_ptr[size_t(v) + 1] - touch_ptr[v] > 1);
 
   // ---- per tile: vertex blob, gather table, contribution groups ---------------------------------
-  P.need.assign(NTILE, 0);
   std::vector<int32_t> deg, order_v, fill_cnt, grp_rel;
-  std::vector<std::vector<int32_t>> tile_cg(NTILE);
+  const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
   for (int tile = 0; tile < NTILE; ++tile) {
     const std::vector<int32_t> &vs = tile_verts[tile];
     const int nv = int(vs.size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
@@ -307,13 +291,13 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     for (int p = 0; p < nv; ++p) slot_of_local[order_v[p]] = p;
     const int ngrp = (nv + 31) / 32;
     grp_rel.assign(size_t(ngrp) + 1, 0);
-    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * deg[order_v[size_t(g) * 32]];  // group length = its largest degree
+    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * ((deg[order_v[size_t(g) * 32]] + 1) & ~1);  // group length = its largest degree, even
     const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
-    while (P.ell.size() % 8) P.ell.push_back(0xFFFF);
+    while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
     if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
     hd->ntet = ntet; hd->nvert = nv; hd->ngrp = ngrp; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
     for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
-    P.ell.resize(size_t(hd->ell_off) + size_t(nell), 0xFFFF);
+    P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
     fill_cnt.assign(nv, 0);
     for (int lt = 0; lt < ntet; ++lt) {
       const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
@@ -321,32 +305,15 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
         if (d[s] == 0xFFFF) continue;
         const int p = slot_of_local[d[s]], g = p >> 5, lane = p & 31;
         const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
-        P.ell[base + size_t(fill_cnt[p]++) * 32 + lane] = uint16_t(s * 3 * TT + lt);  // word offset of component 0
+        const int kk = fill_cnt[p]++;
+        P.ell[base + size_t(kk >> 1) * 64 + size_t(lane) * 2 + (kk & 1)] = uint16_t(s * 3 * TTP + lt);  // word offset of component 0
       }
     }
-    // destinations + owner groups
-    std::vector<int32_t> &cgl = tile_cg[tile];
+    // scratch slot of each staged vertex, in gather-table order
     for (int p = 0; p < nv; ++p) {
       const int32_t v = vs[order_v[p]];
-      const int32_t s = sv_of[v];
-      if (s < 0) {
-        dest[p] = v;
-      } else {
-        const int32_t *tb = &touch[touch_ptr[v]], *te = &touch[touch_ptr[size_t(v) + 1]];
-        const int rank = int(std::lower_bound(tb, te, tile) - tb);
-        dest[p] = -1 - (slot0[s] + rank);
-        const int32_t owner = tb[0];
-        if (std::find(cgl.begin(), cgl.end(), owner) == cgl.end()) { cgl.push_back(owner); P.need[owner]++; }
-      }
-    }
-    hd->ncg = int32_t(cgl.size());
-  }
-  for (int tile = 0; tile < NTILE; ++tile) {
-    TileHeader *hd = reinterpret_cast<TileHeader *>(P.vblob.data() + size_t(tile) * VB);
-    hd->cg_off = int32_t(P.cg.size() / 4);
-    for (int32_t owner : tile_cg[tile]) {
-      P.cg.push_back(owner); P.cg.push_back(P.need[owner]);
-      P.cg.push_back(P.gsv_ptr[owner]); P.cg.push_back(P.gsv_ptr[size_t(owner) + 1]);
+      const int32_t *tb = &touch[touch_ptr[v]], *te = &touch[touch_ptr[size_t(v) + 1]];
+      dest[p] = touch_ptr[v] + int32_t(std::lower_bound(tb, te, tile) - tb);
     }
   }
   return TSB_OK;

@@ -19,16 +19,17 @@ struct TileHeader {
   int32_t ntet;      // tets in this tile (<= fill)
   int32_t nvert;     // vertices staged in shared memory (<= max_local_vertices)
   int32_t ngrp;      // 32-wide vertex groups of the gather table (= ceil(nvert/32))
-  int32_t ncg;       // owner groups this tile contributes shared-vertex partials to
-  int32_t cg_off;    // first entry in cg (int4 records)
   int32_t ell_off;   // first entry in ell (multiple of 8 -> 16-byte aligned)
   int32_t nell;      // gather-table entries, padded to a multiple of 8
-  int32_t pad[9];
+  int32_t pad[11];
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 
 // Vertex blob of one tile (all sections sized by max_local_vertices = NV):
-//   TileHeader | vlist int[NV] | X float[NV] | YZ float2[NV] | dest int[NV] | grp_ptr int[NV/32 + 4]
+//   TileHeader | vlist int[NV] | X float[NV] | YZ float2[NV] | slot int[NV] | grp_ptr int[NV/32 + 4]
+// `slot` (gather-table order) is where the tile's partial gradient of that vertex goes in the
+// float4 scratch array; the slots of one vertex are contiguous (one per touching tile, ascending
+// tile id) so the combine kernel sums them in a fixed order.
 inline int64_t vblob_bytes(int nv) { return 64 + int64_t(20) * nv + 4 * (nv / 32 + 4); }
 // Tet blob of one tile: idx8 (8 x u16)[TT] | B float[9*TT] (tet-major, 9 floats per tet)
 inline int64_t tblob_bytes(int tt) { return int64_t(52) * tt; }
@@ -41,13 +42,10 @@ struct HostPlan {
   std::vector<uint8_t> vblob;   // n_tiles * vblob_bytes(NV)
   std::vector<uint8_t> tblob;   // n_tiles * tblob_bytes(TT)
   // gather table (degree-sorted vertex order inside a tile): word offsets into the kernel's
-  // [24][TT] output table, 0xFFFF = padding; layout [group][k][lane]
+  // [24][TT+4] output table; padding entries point at the table's zero column (offset TT);
+  // layout [group][k/2][lane][2] so one 32-bit load fetches two entries of a lane
   std::vector<uint16_t> ell;
-  // shared-vertex combine (last-arriver per owner tile):
-  std::vector<int32_t> cg;          // int4 records (owner, need[owner], gsv_ptr[owner], gsv_ptr[owner+1])
-  std::vector<int32_t> sv_rec;      // int4 records per shared vertex (global vid, first slot, slot count, 0)
-  std::vector<int32_t> need;        // [n_tiles] contributors per owner group (0 = no group)
-  std::vector<int32_t> gsv_ptr;     // [n_tiles+1] shared vertices owned by each tile
+  std::vector<int32_t> slot_ptr;    // [n+1] scratch slots of each vertex (combine kernel CSR)
   std::vector<int32_t> tet_order;   // tile-order position -> original tet id
   std::vector<int32_t> tile_first;  // [n_tiles+1] position in tet_order of each tile's first tet
 };
