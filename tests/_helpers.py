@@ -46,11 +46,17 @@ class COracle:
 
 _ARRAYS = {"vblob": np.uint8, "tblob": np.uint8, "ell": np.uint16, "slot_ptr": np.int32,
            "tet_order": np.int32, "tile_first": np.int32}
-_HDR = ("ntet", "nvert", "ngrp", "ell_off", "nell")
+_HDR = ("ntet", "nvert", "nrow", "ell_off", "nell")
+ROW_CAP = 16
 
 
-def vblob_bytes(nv):
-    return 64 + 20 * nv + 4 * (nv // 32 + 4)
+def rows_cap(tt, nv):
+    return nv + 8 * tt // ROW_CAP
+
+
+def vblob_bytes(tt, nv):
+    nr = rows_cap(tt, nv)
+    return 64 + 16 * nv + 4 * nr + 4 * (nr // 32 + 4)
 
 
 def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0):
@@ -90,7 +96,7 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0)
         lib.tsb_debug_plan_free(d)
     # unpack the per-tile blobs
     TT, NV = plan["tile_tets"], plan["max_local_vertices"]
-    VB, TB = vblob_bytes(NV), 52 * TT
+    VB, TB, NR = vblob_bytes(TT, NV), 52 * TT, rows_cap(TT, NV)
     tiles = []
     for t in range(plan["n_tiles"]):
         vb = plan["vblob"][t * VB:(t + 1) * VB]
@@ -102,8 +108,8 @@ def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0)
             X=np.stack([vb[64 + 4 * NV:64 + 8 * NV].view(np.float32)[:nv],
                         vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 0],
                         vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 1]], axis=1),
-            slot=vb[64 + 16 * NV:64 + 20 * NV].view(np.int32)[:nv],
-            grp_ptr=vb[64 + 20 * NV:].view(np.int32)[:int(hdr["ngrp"]) + 1],
+            slot=vb[64 + 16 * NV:64 + 16 * NV + 4 * NR].view(np.int32)[:int(hdr["nrow"])],
+            grp_ptr=vb[64 + 16 * NV + 4 * NR:].view(np.int32)[:(int(hdr["nrow"]) + 31) // 32 + 1],
             idx8=tb[:16 * TT].view(np.uint16).reshape(-1, 8)[:nt],
             B=tb[16 * TT:].view(np.float32).reshape(-1, 9)[:nt]))
     plan["tiles"] = tiles
@@ -182,23 +188,21 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
         # phase 2: sliced-ELL gather (entries are word offsets into the [24][TT+4] table, stored as
         # [k/2][lane][2] pairs; padding points at the zero column)
         gp = td["grp_ptr"]
-        ngrp = int(td["ngrp"])
+        nrow = int(td["nrow"])
+        ngrp = (nrow + 31) // 32
         flat = outb.reshape(-1)
-        acc = np.zeros((ngrp * 32, 3), dtype=dtype)
         ell = plan["ell"][td["ell_off"]: td["ell_off"] + td["nell"]]
         n_real = 0
-        for g in range(ngrp):
+        for r in range(nrow):
+            g, lane = r >> 5, r & 31
             blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32, 2).astype(np.int64)
-            for lane in range(32):
-                ent = blk[:, lane, :].reshape(-1)
-                n_real += int((ent != TT).sum())
-                for c in range(3):
-                    acc[g * 32 + lane, c] = flat[ent + c * TTP].sum()
-        assert n_real == int(4 * nt + valid.sum()), "gather table must list every (tet, slot) exactly once"
-        for pidx in range(nv):
-            sl = int(td["slot"][pidx])
+            assert blk.shape[0] * 2 <= ROW_CAP
+            ent = blk[:, lane, :].reshape(-1)
+            n_real += int((ent != TT).sum())
+            sl = int(td["slot"][r])
             assert np.isnan(scratch[sl, 0]), "scratch slot written twice"
-            scratch[sl] = acc[pidx]
+            scratch[sl] = [flat[ent + c * TTP].sum() for c in range(3)]
+        assert n_real == int(4 * nt + valid.sum()), "gather table must list every (tet, slot) exactly once"
     # combine kernel
     sp = plan["slot_ptr"]
     assert sp[0] == 0 and sp[-1] == plan["n_slots"] and not np.isnan(scratch[:plan["n_slots"]]).any()

@@ -92,7 +92,6 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
   if (po.max_local_vertices == 0)
     return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets " + std::to_string(po.tile_tets) + " (compiled: 256, 512, 1024)");
-  po.ell_cap = tsb::ell_cap_for(po.tile_tets);
 
   DeviceGuard guard(device);
   if (!guard.ok) return fail(nullptr, TSB_E_CUDA, "cannot select CUDA device " + std::to_string(device));
@@ -134,7 +133,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   // bytes one launch requests from the memory system: the fixed-size vertex-blob and tet-blob TMA
   // copies, the gather tables, x gathered per staged vertex (12 B), grad (12 B/vertex), the
   // shared-vertex partials written + read back, per-tile energies
-  I.stream_bytes = int64_t(plan.n_tiles) * (tsb::vblob_bytes(plan.max_local_vertices) + int64_t(52) * plan.fill) +
+  I.stream_bytes = int64_t(plan.n_tiles) * (tsb::vblob_bytes(plan.tile_tets, plan.max_local_vertices) + int64_t(52) * plan.fill) +
                    int64_t(plan.ell.size()) * 2 + plan.n_local_vertices * 12 + int64_t(plan.n) * (12 + 4) +
                    int64_t(plan.n_slots) * 32 + int64_t(plan.n_tiles) * 16;
   *out = h;
@@ -226,7 +225,6 @@ int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, 
   po.laplacian_scale = laplacian_scale;
   po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
   if (po.max_local_vertices == 0) return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets");
-  po.ell_cap = tsb::ell_cap_for(po.tile_tets);
   po.balance_sms = balance_sms;
   tsb_debug_plan_s *d = new tsb_debug_plan_s();
   std::string err;
@@ -252,7 +250,7 @@ int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {  /* out8: 10 in
   if (!d || !out8) return TSB_E_INVALID;
   const tsb::HostPlan &P = d->plan;
   out8[0] = P.n; out8[1] = P.nele; out8[2] = P.tile_tets; out8[3] = P.max_local_vertices; out8[4] = P.n_tiles;
-  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots; out8[8] = P.fill; out8[9] = P.ell_cap;
+  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots; out8[8] = P.fill; out8[9] = tsb::ell_cap(P.tile_tets, P.max_local_vertices);
   return TSB_OK;
 }
 

@@ -80,9 +80,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-template <int TT, int NV, int ELLCAP>
+template <int TT, int NV>
 struct Smem {
-  static constexpr int kVBytes = 64 + 20 * NV + 4 * (NV / 32 + 4);
+  static constexpr int NR = NV + 8 * TT / kRowCap;           // == rows_cap(TT, NV)
+  static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;   // == ell_cap(TT, NV)
+  static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
   static constexpr int kVOff = 0;
   static constexpr int kTOff = align_up(kVOff + kVBytes, 128);
   static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
@@ -96,7 +98,7 @@ struct Smem {
 // successive k are 32 words apart.  Padding entries point at the table's zero column.
 template <int TTP>
 __device__ __forceinline__ void gather_vertex(const float *outb, const uint32_t *ep, int len2, float &g0, float &g1, float &g2) {
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < len2; ++k) {
     const uint32_t pr = ep[k * 32];
     const float *o0 = outb + (pr & 0xffffu), *o1 = outb + (pr >> 16);
@@ -105,16 +107,16 @@ __device__ __forceinline__ void gather_vertex(const float *outb, const uint32_t 
   }
 }
 
-template <int TT, int NV, int ELLCAP, int NT, int MINB, bool WITH_GRAD>
+template <int TT, int NV, int NT, int MINB, bool WITH_GRAD>
 __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_constant__ KParams p) {
-  using L = Smem<TT, NV, ELLCAP>;
+  using L = Smem<TT, NV>;
+  constexpr int NR = L::NR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const TileHeader *hd = reinterpret_cast<const TileHeader *>(smem_raw + L::kVOff);
-  const int32_t *vlist_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64);
   const float *Xx_s = reinterpret_cast<const float *>(smem_raw + L::kVOff + 64 + 4 * NV);
   const float2 *xs2 = reinterpret_cast<const float2 *>(smem_raw + L::kVOff + 64 + 8 * NV);     // (Y, Z) rest
   const int32_t *slot_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV);
-  const int32_t *grp_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 20 * NV);
+  const int32_t *grp_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV + 4 * NR);
   const uint4 *idx_s = reinterpret_cast<const uint4 *>(smem_raw + L::kTOff);
   const float *B_s = reinterpret_cast<const float *>(smem_raw + L::kTOff + 16 * TT);
   const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(smem_raw + L::kEllOff);
@@ -126,6 +128,22 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
+
+  // Start the only dependent global chain (vertex id -> x) right away, straight from global memory
+  // and in parallel with the TMA staging below.  Entries past nvert are zero padding (-> x[0]).
+  constexpr int kVPer = (NV + NT - 1) / NT;
+  float px[kVPer][3];
+  {
+    const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(tile) * L::kVBytes + 64);
+    int vid[kVPer];
+#pragma unroll
+    for (int j = 0; j < kVPer; ++j) vid[j] = (tid + j * NT < NV) ? __ldg(vl_g + tid + j * NT) : 0;
+#pragma unroll
+    for (int j = 0; j < kVPer; ++j) {
+      const float *xp = p.x + 3 * size_t(vid[j]);
+      px[j][0] = __ldg(xp); px[j][1] = __ldg(xp + 1); px[j][2] = __ldg(xp + 2);
+    }
+  }
 
   // ---------------- stage the tile with TMA bulk copies ----------------------------------------
   if (tid == 0) {
@@ -143,17 +161,17 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   mbar_wait(&s_bar[0], 0);
   const int ntet = hd->ntet, nvert = hd->nvert;
   const int nell = hd->nell;
-  const bool ell_staged = nell <= ELLCAP;
-  if (WITH_GRAD && tid == 0 && ell_staged && nell > 0) {
+  if (WITH_GRAD && tid == 0 && nell > 0) {
     mbar_expect_tx(&s_bar[2], 2u * uint32_t(nell));
     bulk_g2s(smem_raw + L::kEllOff, p.ell + hd->ell_off, 2u * uint32_t(nell), &s_bar[2]);
   }
 
-  // ---------------- phase 0: gather x --------------------------------------------------------------
+  // ---------------- phase 0: x (prefetched above) + rest X -> shared ---------------------------
   if (WITH_GRAD && tid < 3) outb[tid * TTP + TT] = 0.f;   // zero column for gather-table padding
-  for (int i = tid; i < nvert; i += NT) {
-    const float *xp = p.x + 3 * size_t(vlist_s[i]);
-    xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
+#pragma unroll
+  for (int j = 0; j < kVPer; ++j) {
+    const int i = tid + j * NT;
+    if (i < nvert) xs4[i] = make_float4(px[j][0], px[j][1], px[j][2], Xx_s[i]);
   }
   __syncthreads();
   mbar_wait(&s_bar[1], 0);
@@ -306,17 +324,16 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
 
   if (WITH_GRAD) {
     // ---------------- phase 2: per-vertex gather ------------------------------------------------
-    if (ell_staged && nell > 0) mbar_wait(&s_bar[2], 0);
-    const int ngrp = hd->ngrp;
+    if (nell > 0) mbar_wait(&s_bar[2], 0);
+    const int nrow = hd->nrow;
     float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-    for (int pidx = tid; pidx < ngrp * 32; pidx += NT) {
-      const int g = pidx >> 5, lane = pidx & 31;
+    for (int r = tid; r < nrow; r += NT) {
+      const int g = r >> 5, lane = r & 31;
       const int beg = grp_s[g], end = grp_s[g + 1];
-      const int len2 = (end - beg) >> 6;
+      const int len2 = (end - beg) >> 6;      // <= kRowCap / 2
       float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (ell_staged) gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, len2, g0, g1, g2);
-      else gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(p.ell + size_t(hd->ell_off) + beg) + lane, len2, g0, g1, g2);
-      if (pidx < nvert) scratch4[slot_s[pidx]] = make_float4(g0, g1, g2, 0.f);
+      gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, len2, g0, g1, g2);
+      scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
     }
   }
 }
@@ -436,16 +453,16 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
   }
 }
 
-// Compiled variants: tile capacity TT -> (staged vertices NV, gather-table entries ELLCAP, threads, min CTAs/SM)
-#define TSB_V256 256, 256, 256 * 14
-#define TSB_V512 512, 384, 512 * 11
-#define TSB_V1024 1024, 640, 1024 * 10
+// Compiled variants: tile capacity TT -> staged-vertex capacity NV (then threads, min CTAs/SM)
+#define TSB_V256 256, 256
+#define TSB_V512 512, 384
+#define TSB_V1024 1024, 640
 
-template <int TT, int NV, int ELLCAP, int NT, int MINB>
+template <int TT, int NV, int NT, int MINB>
 cudaError_t launch_variant(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
-  const int smem = Smem<TT, NV, ELLCAP>::kBytes;
-  if (p.grad) energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
-  else energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
+  const int smem = Smem<TT, NV>::kBytes;
+  if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
+  else energy_grad_kernel<TT, NV, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // combine kernel, chained with programmatic dependent launch
@@ -464,12 +481,12 @@ cudaError_t launch_variant(const KParams &p, int n_vertices, const int32_t *slot
   return cudaLaunchKernelEx(&cfg, combine_kernel<CNT>, p, nv, slot_ptr);
 }
 
-template <int TT, int NV, int ELLCAP, int NT, int MINB>
+template <int TT, int NV, int NT, int MINB>
 cudaError_t prepare_variant() {
-  const int smem = Smem<TT, NV, ELLCAP>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = Smem<TT, NV>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NV, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(energy_grad_kernel<TT, NV, ELLCAP, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return cudaFuncSetAttribute(energy_grad_kernel<TT, NV, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 inline int grid_for(int64_t count, int block) {
@@ -484,15 +501,6 @@ int nvmax_for(int tile_tets) {
     case 256: return 256;
     case 512: return 384;
     case 1024: return 640;
-  }
-  return 0;
-}
-
-int ell_cap_for(int tile_tets) {
-  switch (tile_tets) {
-    case 256: return 256 * 14;
-    case 512: return 512 * 11;
-    case 1024: return 1024 * 10;
   }
   return 0;
 }

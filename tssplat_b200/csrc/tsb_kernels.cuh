@@ -33,7 +33,6 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 // One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
 cudaError_t prepare_energy_grad(int tile_tets);
 int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
-int ell_cap_for(int tile_tets);   // gather-table entries the variant stages in shared memory
 void set_threads_512(int nt);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);

@@ -200,10 +200,10 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   }
   const int NTILE = int(P.tile_first.size()) - 1;
   P.n_tiles = NTILE;
-  const int64_t VB = vblob_bytes(NVMAX), TB = tblob_bytes(TT);
+  const int64_t VB = vblob_bytes(TT, NVMAX), TB = tblob_bytes(TT);
+  const int NR = rows_cap(TT, NVMAX);
   P.vblob.assign(size_t(NTILE) * VB, 0);
   P.tblob.assign(size_t(NTILE) * TB, 0);
-  P.ell_cap = opt.ell_cap > 0 ? opt.ell_cap : 8 * TT + 1024;
 
   // ---- per tile: staged vertex list (id-sorted), local stencil ids, rest inverses ---------------
   std::vector<int32_t> local_of(n, -1);
@@ -243,77 +243,101 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     }
   }
 
-  // ---- vertex -> touching tiles (ascending tile id), shared vertices, owners, scratch slots -----
-  std::vector<int32_t> touch_ptr(size_t(n) + 1, 0);
-  for (int tile = 0; tile < NTILE; ++tile)
-    for (int32_t v : tile_verts[tile]) touch_ptr[size_t(v) + 1]++;
-  for (int v = 0; v < n; ++v) touch_ptr[size_t(v) + 1] += touch_ptr[v];
-  std::vector<int32_t> touch(size_t(touch_ptr[n]));
-  {
-    std::vector<int32_t> cur(touch_ptr.begin(), touch_ptr.end() - 1);
-    for (int tile = 0; tile < NTILE; ++tile)
-      for (int32_t v : tile_verts[tile]) touch[size_t(cur[v]++)] = tile;
+  // ---- in-tile degree of every staged vertex -> gather-table rows -> scratch slots ----------------
+  // rows_of[tile][i] = ceil(deg / kRowCap) for the i-th staged vertex (id-sorted)
+  std::vector<std::vector<int32_t>> tile_deg(NTILE);
+  for (int tile = 0; tile < NTILE; ++tile) {
+    const int nv = int(tile_verts[tile].size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
+    std::vector<int32_t> &dg = tile_deg[tile];
+    dg.assign(nv, 0);
+    for (int lt = 0; lt < ntet; ++lt) {
+      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
+      for (int s = 0; s < 8; ++s) if (d[s] != 0xFFFF) dg[d[s]]++;
+    }
   }
-  // scratch slots: one per (vertex, touching tile), contiguous per vertex
-  P.slot_ptr.assign(touch_ptr.begin(), touch_ptr.end());
-  P.n_slots = touch_ptr[n];
-  for (int v = 0; v < n; ++v) P.n_shared_vertices += (touch_ptr[size_t(v) + 1] - touch_ptr[v] > 1);
-
-  // ---- per tile: vertex blob, gather table, contribution groups ---------------------------------
-  std::vector<int32_t> deg, order_v, fill_cnt, grp_rel;
-  const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
+  // slot_ptr[v]..slot_ptr[v+1]: scratch slots of vertex v, ordered by (tile, row)
+  P.slot_ptr.assign(size_t(n) + 1, 0);
+  std::vector<int32_t> touches(n, 0);
   for (int tile = 0; tile < NTILE; ++tile) {
     const std::vector<int32_t> &vs = tile_verts[tile];
+    for (size_t i = 0; i < vs.size(); ++i) {
+      P.slot_ptr[size_t(vs[i]) + 1] += (tile_deg[tile][i] + kRowCap - 1) / kRowCap;
+      touches[vs[i]]++;
+    }
+  }
+  for (int v = 0; v < n; ++v) {
+    P.slot_ptr[size_t(v) + 1] += P.slot_ptr[v];
+    P.n_shared_vertices += touches[v] > 1;
+  }
+  if (int64_t(P.slot_ptr[n]) > int64_t(0x7fffffff) / 4) { err = "too many scratch slots"; return TSB_E_INVALID; }
+  P.n_slots = P.slot_ptr[n];
+  std::vector<int32_t> next_slot(P.slot_ptr.begin(), P.slot_ptr.end() - 1);   // tiles visited in ascending order
+
+  // ---- per tile: vertex blob, gather table ---------------------------------------------------------
+  const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
+  struct Row { int32_t vert, chunk, len; };
+  std::vector<Row> rows;
+  std::vector<int32_t> grp_rel, fill_cnt;
+  for (int tile = 0; tile < NTILE; ++tile) {
+    const std::vector<int32_t> &vs = tile_verts[tile];
+    const std::vector<int32_t> &dg = tile_deg[tile];
     const int nv = int(vs.size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
     uint8_t *vb = P.vblob.data() + size_t(tile) * VB;
     TileHeader *hd = reinterpret_cast<TileHeader *>(vb);
     int32_t *vlist = reinterpret_cast<int32_t *>(vb + 64);
     float *Xx = reinterpret_cast<float *>(vb + 64 + size_t(4) * NVMAX);
     float *YZ = reinterpret_cast<float *>(vb + 64 + size_t(8) * NVMAX);
-    int32_t *dest = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX);
-    int32_t *grp_ptr = reinterpret_cast<int32_t *>(vb + 64 + size_t(20) * NVMAX);
+    int32_t *slot = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX);
+    int32_t *grp_ptr = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX + size_t(4) * NR);
     for (int i = 0; i < nv; ++i) {
       vlist[i] = vs[i];
       Xx[i] = rest[3 * size_t(vs[i])];
       YZ[2 * i] = rest[3 * size_t(vs[i]) + 1];
       YZ[2 * i + 1] = rest[3 * size_t(vs[i]) + 2];
     }
-    // in-tile degree of each staged vertex (number of (tet, slot) entries that add into it)
-    deg.assign(nv, 0);
-    for (int lt = 0; lt < ntet; ++lt) {
-      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
-      for (int s = 0; s < 8; ++s) if (d[s] != 0xFFFF) deg[d[s]]++;
+    // rows, longest first (stable: vertex id, then chunk)
+    rows.clear();
+    for (int i = 0; i < nv; ++i) {
+      const int nr = (dg[i] + kRowCap - 1) / kRowCap;
+      for (int c = 0; c < nr; ++c) rows.push_back(Row{i, c, std::min(kRowCap, dg[i] - c * kRowCap)});
     }
-    order_v.resize(nv);
-    std::iota(order_v.begin(), order_v.end(), 0);
-    std::stable_sort(order_v.begin(), order_v.end(), [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
-    std::vector<int32_t> slot_of_local(nv);  // local vertex -> position in the gather table
-    for (int p = 0; p < nv; ++p) slot_of_local[order_v[p]] = p;
-    const int ngrp = (nv + 31) / 32;
+    std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.len > b.len; });
+    const int nrow = int(rows.size());
+    if (nrow > NR) { err = "internal: gather-table rows exceed capacity"; return TSB_E_INVALID; }
+    const int ngrp = (nrow + 31) / 32;
     grp_rel.assign(size_t(ngrp) + 1, 0);
-    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * ((deg[order_v[size_t(g) * 32]] + 1) & ~1);  // group length = its largest degree, even
+    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * ((rows[size_t(g) * 32].len + 1) & ~1);
     const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
+    if (nell > ell_cap(TT, NVMAX)) { err = "internal: gather table exceeds capacity"; return TSB_E_INVALID; }
     while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
     if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
-    hd->ntet = ntet; hd->nvert = nv; hd->ngrp = ngrp; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
+    hd->ntet = ntet; hd->nvert = nv; hd->nrow = nrow; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
     for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
     P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
+    // row index of (vertex, chunk 0); chunks of a vertex are NOT adjacent after sorting, so map each
+    std::vector<std::vector<int32_t>> row_of(nv);
+    for (int r = 0; r < nrow; ++r) {
+      std::vector<int32_t> &ro = row_of[rows[r].vert];
+      if (int(ro.size()) <= rows[r].chunk) ro.resize(size_t(rows[r].chunk) + 1, -1);
+      ro[rows[r].chunk] = r;
+    }
     fill_cnt.assign(nv, 0);
     for (int lt = 0; lt < ntet; ++lt) {
       const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
       for (int s = 0; s < 8; ++s) {
         if (d[s] == 0xFFFF) continue;
-        const int p = slot_of_local[d[s]], g = p >> 5, lane = p & 31;
+        const int cnt = fill_cnt[d[s]]++;
+        const int r = row_of[d[s]][cnt / kRowCap], kk = cnt % kRowCap;
+        const int g = r >> 5, lane = r & 31;
         const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
-        const int kk = fill_cnt[p]++;
         P.ell[base + size_t(kk >> 1) * 64 + size_t(lane) * 2 + (kk & 1)] = uint16_t(s * 3 * TTP + lt);  // word offset of component 0
       }
     }
-    // scratch slot of each staged vertex, in gather-table order
-    for (int p = 0; p < nv; ++p) {
-      const int32_t v = vs[order_v[p]];
-      const int32_t *tb = &touch[touch_ptr[v]], *te = &touch[touch_ptr[size_t(v) + 1]];
-      dest[p] = touch_ptr[v] + int32_t(std::lower_bound(tb, te, tile) - tb);
+    // scratch slot of each row: vertex's slots are ordered by (tile, chunk)
+    for (int i = 0; i < nv; ++i) {
+      const int nr = int(row_of[i].size());
+      for (int c = 0; c < nr; ++c) slot[row_of[i][c]] = next_slot[vs[i]] + c;
+      next_slot[vs[i]] += nr;
     }
   }
   return TSB_OK;

@@ -18,25 +18,30 @@ namespace tsb {
 struct TileHeader {
   int32_t ntet;      // tets in this tile (<= fill)
   int32_t nvert;     // vertices staged in shared memory (<= max_local_vertices)
-  int32_t ngrp;      // 32-wide vertex groups of the gather table (= ceil(nvert/32))
+  int32_t nrow;      // gather-table rows (a vertex with more than kRowCap entries spans several rows)
   int32_t ell_off;   // first entry in ell (multiple of 8 -> 16-byte aligned)
   int32_t nell;      // gather-table entries, padded to a multiple of 8
   int32_t pad[11];
 };
 static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 
-// Vertex blob of one tile (all sections sized by max_local_vertices = NV):
-//   TileHeader | vlist int[NV] | X float[NV] | YZ float2[NV] | slot int[NV] | grp_ptr int[NV/32 + 4]
-// `slot` (gather-table order) is where the tile's partial gradient of that vertex goes in the
-// float4 scratch array; the slots of one vertex are contiguous (one per touching tile, ascending
-// tile id) so the combine kernel sums them in a fixed order.
-inline int64_t vblob_bytes(int nv) { return 64 + int64_t(20) * nv + 4 * (nv / 32 + 4); }
+// Gather-table rows hold at most kRowCap entries, so one hub vertex cannot serialise a warp; a
+// vertex with in-tile degree d owns ceil(d / kRowCap) rows, each with its own scratch slot.
+constexpr int kRowCap = 16;
+inline int rows_cap(int tt, int nv) { return nv + 8 * tt / kRowCap; }           // rows per tile upper bound
+inline int ell_cap(int tt, int nv) { return 8 * tt + 32 * kRowCap + rows_cap(tt, nv) + 64; }  // entries upper bound
+// Vertex blob of one tile (NV = max_local_vertices, NR = rows_cap):
+//   TileHeader | vlist int[NV] | X float[NV] | YZ float2[NV] | slot int[NR] | grp_ptr int[NR/32 + 4]
+// `slot` (row order) is where the row's partial gradient goes in the float4 scratch array; the
+// slots of one vertex are contiguous (ascending tile id, then row) so the combine kernel sums
+// them in a fixed order.
+inline int64_t vblob_bytes(int tt, int nv) { return 64 + int64_t(16) * nv + 4 * rows_cap(tt, nv) + 4 * (rows_cap(tt, nv) / 32 + 4); }
 // Tet blob of one tile: idx8 (8 x u16)[TT] | B float[9*TT] (tet-major, 9 floats per tet)
 inline int64_t tblob_bytes(int tt) { return int64_t(52) * tt; }
 
 struct HostPlan {
   int32_t n = 0, nele = 0, tile_tets = 0, fill = 0, max_local_vertices = 0, n_tiles = 0, n_components = 0;
-  int32_t laplacian_scale = 0, n_boundary_faces = 0, n_shared_vertices = 0, n_slots = 0, ell_cap = 0;
+  int32_t laplacian_scale = 0, n_boundary_faces = 0, n_shared_vertices = 0, n_slots = 0;
   int64_t n_local_vertices = 0;
 
   std::vector<uint8_t> vblob;   // n_tiles * vblob_bytes(NV)
@@ -55,7 +60,6 @@ struct PlanOptions {
   int32_t max_local_vertices = 384; // capacity NV of the compiled kernel variant
   int32_t laplacian_scale = 0;
   int32_t balance_sms = 148;        // >0: pick the tile fill so the tile count is a multiple of this
-  int32_t ell_cap = 0;              // gather-table entries the kernel can stage in smem (0 = 8*TT+1024)
 };
 
 // Returns 0 on success, TSB_E_* otherwise (message in err).
