@@ -256,6 +256,10 @@ int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {  /* out8: 10 in
 
 void tsb_debug_plan_free(tsb_debug_plan_s *d) { delete d; }
 
+/* Developer tool: device buffer of [n_tiles][16] int64 phase stamps written by the next launches
+ * (NULL switches it off).  Not part of the stable ABI. */
+void tsb_debug_set_timing(tsb_handle_t h, long long *dbg_dev) { if (h) h->kp.dbg = dbg_dev; }
+
 /* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
 void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
 

@@ -80,6 +80,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
+#define TSB_STAMP(slot) do { if (p.dbg && tid == 0) p.dbg[size_t(tile) * 16 + (slot)] = clock64(); } while (0)
+
 template <int TT, int NV>
 struct Smem {
   static constexpr int NR = NV + 8 * TT / kRowCap;           // == rows_cap(TT, NV)
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
 
+  if (p.dbg && tid == 0) { p.dbg[size_t(tile) * 16 + 14] = gtime_ns(); p.dbg[size_t(tile) * 16 + 13] = smid(); }
+  TSB_STAMP(0);
   // Start the only dependent global chain (vertex id -> x) right away, straight from global memory
   // and in parallel with the TMA staging below.  Entries past nvert are zero padding (-> x[0]).
   constexpr int kVPer = (NV + NT - 1) / NT;
@@ -158,7 +164,9 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &s_bar[1]);
   }
   __syncthreads();
+  TSB_STAMP(1);
   mbar_wait(&s_bar[0], 0);
+  TSB_STAMP(2);
   const int ntet = hd->ntet, nvert = hd->nvert;
   const int nell = hd->nell;
   if (WITH_GRAD && tid == 0 && nell > 0) {
@@ -173,8 +181,11 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     const int i = tid + j * NT;
     if (i < nvert) xs4[i] = make_float4(px[j][0], px[j][1], px[j][2], Xx_s[i]);
   }
+  TSB_STAMP(3);
   __syncthreads();
+  TSB_STAMP(4);
   mbar_wait(&s_bar[1], 0);
+  TSB_STAMP(5);
 
   // ---------------- phase 1: tets -----------------------------------------------------------------
   float es = 0.f, eb = 0.f;
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     }
   }
 
+  TSB_STAMP(6);
   // per-tile energy partials (tree reduction; the cross-tile sum is done in fp64 below)
   {
     const float ws = warp_sum(es), wb = warp_sum(eb);
@@ -324,7 +336,9 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
 
   if (WITH_GRAD) {
     // ---------------- phase 2: per-vertex gather ------------------------------------------------
+    TSB_STAMP(7);
     if (nell > 0) mbar_wait(&s_bar[2], 0);
+    TSB_STAMP(8);
     const int nrow = hd->nrow;
     float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
     for (int r = tid; r < nrow; r += NT) {
@@ -335,7 +349,9 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
       gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, len2, g0, g1, g2);
       scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
     }
+    TSB_STAMP(9);
   }
+  if (p.dbg && tid == 0) p.dbg[size_t(tile) * 16 + 15] = gtime_ns();
 }
 
 // Combine kernel: grad[v] = gradH * sum of v's scratch slots (fixed order); block 0 also folds the

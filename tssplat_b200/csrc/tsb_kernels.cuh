@@ -26,6 +26,7 @@ struct KParams {
   int32_t laplacian_scale;
   int32_t n_tiles;
   int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
+  long long *dbg;               // optional [n_tiles][16] phase timestamps (developer tool), else nullptr
 };
 
 // Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
