@@ -138,17 +138,11 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   // Start the only dependent global chain (vertex id -> x) right away, straight from global memory
   // and in parallel with the TMA staging below.  Entries past nvert are zero padding (-> x[0]).
   constexpr int kVPer = (NV + NT - 1) / NT;
-  float px[kVPer][3];
+  int vid[kVPer];
   {
     const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(tile) * L::kVBytes + 64);
-    int vid[kVPer];
 #pragma unroll
     for (int j = 0; j < kVPer; ++j) vid[j] = (tid + j * NT < NV) ? __ldg(vl_g + tid + j * NT) : 0;
-#pragma unroll
-    for (int j = 0; j < kVPer; ++j) {
-      const float *xp = p.x + 3 * size_t(vid[j]);
-      px[j][0] = __ldg(xp); px[j][1] = __ldg(xp + 1); px[j][2] = __ldg(xp + 2);
-    }
   }
 
   // ---------------- stage the tile with TMA bulk copies ----------------------------------------
@@ -162,6 +156,12 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
     bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &s_bar[1]);
     bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &s_bar[1]);
+  }
+  float px[kVPer][3];
+#pragma unroll
+  for (int j = 0; j < kVPer; ++j) {
+    const float *xp = p.x + 3 * size_t(vid[j]);
+    px[j][0] = __ldg(xp); px[j][1] = __ldg(xp + 1); px[j][2] = __ldg(xp + 2);
   }
   __syncthreads();
   TSB_STAMP(1);

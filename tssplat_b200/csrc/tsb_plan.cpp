@@ -277,7 +277,8 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
   struct Row { int32_t vert, chunk, len; };
   std::vector<Row> rows;
-  std::vector<int32_t> grp_rel, fill_cnt;
+  std::vector<int32_t> grp_rel, fill_cnt, row_n;
+  std::vector<uint16_t> row_ent;
   for (int tile = 0; tile < NTILE; ++tile) {
     const std::vector<int32_t> &vs = tile_verts[tile];
     const std::vector<int32_t> &dg = tile_deg[tile];
@@ -321,16 +322,52 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       if (int(ro.size()) <= rows[r].chunk) ro.resize(size_t(rows[r].chunk) + 1, -1);
       ro[rows[r].chunk] = r;
     }
+    // collect each row's entries (word offset of component 0 in the [24][TTP] table)
+    row_ent.assign(size_t(nrow) * kRowCap, 0);
+    row_n.assign(nrow, 0);
     fill_cnt.assign(nv, 0);
     for (int lt = 0; lt < ntet; ++lt) {
       const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
       for (int s = 0; s < 8; ++s) {
         if (d[s] == 0xFFFF) continue;
         const int cnt = fill_cnt[d[s]]++;
-        const int r = row_of[d[s]][cnt / kRowCap], kk = cnt % kRowCap;
-        const int g = r >> 5, lane = r & 31;
-        const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
-        P.ell[base + size_t(kk >> 1) * 64 + size_t(lane) * 2 + (kk & 1)] = uint16_t(s * 3 * TTP + lt);  // word offset of component 0
+        const int r = row_of[d[s]][cnt / kRowCap];
+        row_ent[size_t(r) * kRowCap + row_n[r]++] = uint16_t(s * 3 * TTP + lt);
+      }
+    }
+    // Order the entries of the 32 rows of a group so that, column by column, the 32 lanes of the
+    // warp read distinct shared-memory banks (bank = word offset mod 32; the three components
+    // are +TTP words apart, i.e. the same permutation shifted).  Greedy column-by-column
+    // matching, rows with the fewest remaining entries first within a column.
+    for (int g = 0; g < ngrp; ++g) {
+      const int r0 = g * 32, r1 = std::min(nrow, r0 + 32);
+      const int glen = (grp_rel[g + 1] - grp_rel[g]) / 32;
+      const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
+      uint8_t used_e[32][kRowCap] = {};
+      for (int k = 0; k < glen; ++k) {
+        uint32_t bank_used = 0;
+        // two passes: first place rows that can take a free bank, then the rest
+        int pending[32], np = 0;
+        for (int r = r0; r < r1; ++r) {
+          if (k >= row_n[r]) continue;   // this row is already exhausted -> padding (zero column)
+          int pick = -1;
+          for (int e = 0; e < row_n[r]; ++e) {
+            if (used_e[r - r0][e]) continue;
+            const int bank = row_ent[size_t(r) * kRowCap + e] & 31;
+            if (!(bank_used >> bank & 1u)) { pick = e; break; }
+          }
+          if (pick < 0) { pending[np++] = r; continue; }
+          used_e[r - r0][pick] = 1;
+          bank_used |= 1u << (row_ent[size_t(r) * kRowCap + pick] & 31);
+          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
+        }
+        for (int q = 0; q < np; ++q) {
+          const int r = pending[q];
+          int pick = -1;
+          for (int e = 0; e < row_n[r] && pick < 0; ++e) if (!used_e[r - r0][e]) pick = e;
+          used_e[r - r0][pick] = 1;
+          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
+        }
       }
     }
     // scratch slot of each row: vertex's slots are ordered by (tile, chunk)
