@@ -1,0 +1,250 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the fp64 C oracle, the committed golden fixtures and size-independent properties.
+
+Tolerance: BASELINE.json's north_star asks for outputs within 1e-5 relative (fp32) of the
+reference; here relative energy error <= 1e-5 and relative gradient L2 error <= 1e-5 against the
+fp64 restatement (the reference itself cannot run here; parity vs its binary is unpinned)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _helpers import GOLDEN, COracle
+from tssplat_b200.mesh import concat_spheres, make_pack, make_tet_sphere, perturb
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ext():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from tssplat_b200 import tet_spheres_ext
+    return tet_spheres_ext
+
+
+def _check(ext, verts, tets, x_np, c1, c2, order, gradH=1.0, tile_tets=0, scale=0, rel=REL):
+    sp = ext.TetSpheres(np.ascontiguousarray(verts, dtype=np.float32).reshape(-1),
+                        np.ascontiguousarray(tets, dtype=np.int32).reshape(-1), tile_tets=tile_tets,
+                        laplacian_scale=scale)
+    x = torch.from_numpy(np.asarray(x_np, dtype=np.float32)).cuda()
+    e, g = sp.energy_grad(x, c1, c2, order, gradH)
+    torch.cuda.synchronize()
+    eo, terms, go = COracle(verts, tets, scale).energy_grad(x_np, c1, c2, order, gradH=gradH)
+    e = e.cpu().numpy().astype(np.float64)
+    g = g.cpu().numpy().astype(np.float64)
+    assert not np.isnan(g).any()
+    assert abs(e[0] - eo) <= rel * max(abs(eo), 1e-30), (e[0], eo)
+    assert abs(e[1] - terms[0]) <= rel * max(abs(terms[0]), 1e-30)
+    assert abs(e[2] - terms[1]) <= rel * max(abs(terms[1]), 1e-30)
+    assert np.linalg.norm(g - go) <= rel * np.linalg.norm(go), np.linalg.norm(g - go) / np.linalg.norm(go)
+    return sp, e, g
+
+
+@pytest.mark.parametrize("tile_tets", [256, 512, 1024])
+@pytest.mark.parametrize("sig,order", [(0.02, 2), (0.35, 2), (0.35, 4)])
+def test_parity_small_pack(ext, tile_tets, sig, order):
+    pack = make_pack(3, 1024, seed=1)
+    _check(ext, pack.verts, pack.tets, perturb(pack, sigma_rel=sig, seed=1), 2e-4 / 3, 2e-4, order,
+           gradH=0.7, tile_tets=tile_tets)
+
+
+def test_parity_coefficient_range_and_scale(ext):
+    """c multipliers 1 and 16 (energies/smooth_barrier.py:50-54) and the scaled Laplacian."""
+    pack = make_pack(2, 1500, seed=4)                     # ragged: 1500 is not a tile multiple
+    x = perturb(pack, sigma_rel=0.35, seed=3)
+    for m in (1.0, 16.0):
+        _check(ext, pack.verts, pack.tets, x, 2e-4 / 2 * m, 2e-4 * m, 2)
+    _check(ext, pack.verts, pack.tets, x, 1e-3, 1e-3, 4, scale=1)
+
+
+def test_parity_16_spheres(ext):
+    """BASELINE.json configs[1]: 16 tet-spheres, fused energy+grad kernel only, fp32."""
+    pack = make_pack(16, 4096, seed=0, unique=4)
+    for sig, order in ((0.02, 2), (0.35, 4)):
+        _check(ext, pack.verts, pack.tets, perturb(pack, sigma_rel=sig, seed=1), 2e-4 / 16, 2e-4, order)
+
+
+def test_golden_fixtures(ext):
+    gold = np.load(os.path.join(GOLDEN, "golden_energy.npz"))
+    d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
+    pk = make_pack(3, 1024, seed=1)
+    meshes = {"a_veg": (d["verts"], d["tets"]), "pack3x1024": (pk.verts.astype(np.float64), pk.tets)}
+    cases = {"benign_o2": (0.02, 0, 2, 2e-4, 2e-4, 1.0), "inverted_o2": (0.35, 1, 2, 3.2e-3, 3.2e-3, 0.5),
+             "inverted_o4": (0.35, 1, 4, 2e-4, 2e-4, 1.0)}
+    for mname, (v, t) in meshes.items():
+        for cname, (sig, seed, order, c1, c2, gh) in cases.items():
+            x = perturb(v, t, sig, seed)
+            _, e, g = _check(ext, v, t, x, c1, c2, order, gradH=gh)
+            k = f"{mname}/{cname}"
+            assert e[0] == pytest.approx(float(gold[k + "/energy"]), rel=REL)
+            assert np.linalg.norm(g) == pytest.approx(float(gold[k + "/grad_l2"]), rel=REL)
+            samp = g[:: max(1, len(g) // 64)][:64]
+            assert np.abs(samp - gold[k + "/grad_sample"]).max() <= 1e-5 * np.abs(gold[k + "/grad_sample"]).max()
+
+
+def test_known_answers(ext):
+    v, t = make_tet_sphere(1003, 512)
+    v = v.astype(np.float32)
+    sp = ext.TetSpheres(v.reshape(-1), t.reshape(-1))
+
+    def run(x, c1=1.0, c2=1.0, order=2):
+        e, g = sp.energy_grad(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda(), c1, c2, order)
+        return e.cpu().numpy().astype(np.float64), g.cpu().numpy()
+    e, g = run(v)                                          # rest state
+    assert abs(e[0]) < 1e-7 and np.abs(g).max() < 1e-4
+    A = np.array([[1.1, 0.2, 0.0], [0.0, 0.9, 0.1], [0.1, 0.0, 1.2]])
+    e, _ = run(v.astype(np.float64) @ A.T + 0.3)           # affine map: L F = 0, det > 0
+    assert abs(e[0]) < 1e-6 * len(t)
+    xr = v * np.array([1, 1, -1], dtype=np.float32)        # reflection: det F = -1 in every tet
+    for order in (2, 4):
+        e, _ = run(xr, 1.0, 0.25, order)
+        assert e[2] == pytest.approx(len(t), rel=1e-5) and e[0] == pytest.approx(0.25 * len(t), rel=1e-5)
+
+
+def test_tiny_and_unreferenced(ext):
+    v1 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [9, 9, 9]], dtype=np.float32)  # vertex 4 unused
+    t1 = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    x = v1 * np.array([1, 1, -1.5], dtype=np.float32)
+    sp, e, g = _check(ext, v1, t1, x, 1.0, 1.0, 2)
+    assert e[1] == 0.0 and e[2] == pytest.approx(2.25, rel=1e-6) and np.all(g[4] == 0.0)
+    v2 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], dtype=np.float32)
+    t2 = np.array([[0, 1, 2, 3], [1, 3, 2, 4]], dtype=np.int32)
+    _check(ext, v2, t2, perturb(v2, t2, 0.3, 1), 0.7, 0.3, 2)
+
+
+def test_deterministic_and_reentrant_handles(ext):
+    pack = make_pack(4, 2048, seed=6)
+    x = torch.from_numpy(perturb(pack, sigma_rel=0.35, seed=5)).cuda()
+    a = ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1))
+    b = ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1), tile_tets=256)
+    e1, g1 = a.energy_grad(x, 1e-4, 2e-4, 2)
+    eb, gb = b.energy_grad(x, 1e-4, 2e-4, 2)
+    e2, g2 = a.energy_grad(x, 1e-4, 2e-4, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(g1, g2) and torch.equal(e1, e2)                  # bitwise repeatable
+    assert torch.allclose(g1, gb, rtol=1e-4, atol=1e-7)                  # other tiling: same answer
+    del a, b
+
+
+def test_autograd_surface(ext):
+    """The reference's Python surface: SmoothnessBarrierEnergy / SmoothnessBarrierFunc
+    (energies/smooth_barrier.py:9-67) as trainer.py / tetmesh_geometry.py use it."""
+    from tssplat_b200.energies import SmoothnessBarrierEnergy
+    pack = make_pack(3, 1024, seed=2)
+    flags = dict(smooth_eng_coeff=2e-4 / 3, barrier_coeff=2e-4, increase_order_iter=1000)
+    eng = SmoothnessBarrierEnergy(pack.verts, pack.tets, flags)
+    x_np = perturb(pack, sigma_rel=0.35, seed=2)
+    orc = COracle(pack.verts, pack.tets)
+    for it in (10, 1500):                                    # order 2, then order 4 (smooth_barrier.py:61-63)
+        tet_v = torch.nn.Parameter(torch.from_numpy(x_np).cuda())
+        c1, c2 = eng.coeff_scheduler(it)
+        e = eng(tet_v, it, c1, c2)
+        assert e.dim() == 0 and e.is_cuda
+        loss = 3.0 * e + 1.0                                 # grad_output = 3 arrives as a CUDA scalar
+        loss.backward()
+        order = 4 if it > 1000 else 2
+        eo, _, go = orc.energy_grad(x_np, c1, c2, order, gradH=3.0)
+        assert float(e) == pytest.approx(eo, rel=REL)
+        g = tet_v.grad.cpu().numpy().astype(np.float64)
+        assert tet_v.grad.shape == (pack.n, 3) and np.linalg.norm(g - go) <= REL * np.linalg.norm(go)
+    # stale-cache protection: modify x in place between forward and backward -> backward recomputes
+    tet_v = torch.nn.Parameter(torch.from_numpy(x_np).cuda())
+    e = eng(tet_v, 10, 1e-4, 2e-4)
+    with torch.no_grad():
+        tet_v.mul_(1.0)                                      # bumps the version counter
+    g_direct = ext.backward(torch.tensor(1.0), tet_v, eng.tet_sp, 1e-4, 2e-4, 2)   # CPU grad_output, like the reference
+    _, _, go = orc.energy_grad(x_np, 1e-4, 2e-4, 2)
+    assert np.linalg.norm(g_direct.cpu().numpy() - go) <= REL * np.linalg.norm(go)
+    # reference-style CPU scalar on request; no-grad forward skips the gradient
+    ext.return_cpu_scalar = True
+    try:
+        with torch.no_grad():
+            e_cpu = ext.forward(tet_v.detach(), eng.tet_sp, 1e-4, 2e-4, 2)
+        assert not e_cpu.is_cuda and e_cpu.dim() == 0
+    finally:
+        ext.return_cpu_scalar = False
+    assert ext.random_x(eng.tet_sp).shape == (pack.n, 3)
+
+
+def test_error_behaviour(ext):
+    v, t = make_tet_sphere(1005, 128)
+    sp = ext.TetSpheres(v.astype(np.float32).reshape(-1), t.reshape(-1))
+    x = torch.from_numpy(v.astype(np.float32)).cuda()
+    with pytest.raises(RuntimeError, match="order"):
+        sp.energy_grad(x, 1.0, 1.0, 3)
+    with pytest.raises(RuntimeError):
+        sp.energy_grad(x.double(), 1.0, 1.0, 2)
+    with pytest.raises(RuntimeError):
+        sp.energy_grad(x.cpu(), 1.0, 1.0, 2)
+    with pytest.raises(RuntimeError):
+        sp.energy_grad(x[:-1], 1.0, 1.0, 2)
+    with pytest.raises(RuntimeError, match="zero rest volume"):
+        ext.TetSpheres(np.zeros(12, dtype=np.float32), np.array([0, 1, 2, 3], dtype=np.int32))
+    with pytest.raises(RuntimeError):
+        ext.TetSpheres(v.astype(np.float64).reshape(-1), t.reshape(-1))           # wrong dtype
+
+
+def test_full_size_properties_64_spheres(ext):
+    """BASELINE.json's headline size (64 x 4096 tets): oracle parity plus properties that do not
+    need an oracle -- rigid-motion invariance, zero net force per sphere, block-diagonality."""
+    pack = make_pack(64, 4096, seed=0, unique=8)
+    x_np = perturb(pack, sigma_rel=0.35, seed=1)
+    c1, c2 = 2e-4 / 64, 2e-4
+    sp, e, g = _check(ext, pack.verts, pack.tets, x_np, c1, c2, 2)
+    # zero net force on every sphere (translation invariance)
+    for s in range(pack.num_spheres):
+        v0, v1 = pack.vert_offsets[s], pack.vert_offsets[s + 1]
+        assert np.abs(g[v0:v1].sum(axis=0)).max() <= 2e-4 * np.abs(g[v0:v1]).sum(axis=0).max()
+    # rigid motion leaves the energy unchanged and rotates the gradient
+    q, _ = np.linalg.qr(np.random.default_rng(0).normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    xr = (x_np.astype(np.float64) @ q.T + np.array([0.3, -0.2, 0.1])).astype(np.float32)
+    e2, g2 = sp.energy_grad(torch.from_numpy(xr).cuda(), c1, c2, 2)
+    assert float(e2[0]) == pytest.approx(e[0], rel=2e-5)
+    g2 = g2.cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(g2 - g @ q.T) <= 5e-5 * np.linalg.norm(g)
+    # block-diagonality: spheres 10..13 as their own handle give the same gradient slice
+    sub = pack.slice_spheres(10, 14)
+    v0, v1 = int(pack.vert_offsets[10]), int(pack.vert_offsets[14])
+    sps = ext.TetSpheres(sub.verts.reshape(-1), sub.tets.reshape(-1))
+    es, gs = sps.energy_grad(torch.from_numpy(x_np[v0:v1]).cuda(), c1, c2, 2)
+    assert np.linalg.norm(gs.cpu().numpy() - g[v0:v1]) <= 2e-5 * np.linalg.norm(g[v0:v1])
+
+
+def test_grad_limit_and_adam_uniform(ext):
+    from tssplat_b200 import _capi
+    torch.manual_seed(0)
+    g = torch.randn(1000, 3, device="cuda") * 0.01
+    ref = g.clone()
+    ext.grad_limit(g, 0.5, 0.05)                                            # below threshold: untouched
+    assert torch.equal(g, ref)
+    ext.grad_limit(g, 0.001, 0.05)                                          # scale so that max|g| = s
+    assert float(g.abs().max()) == pytest.approx(0.05, rel=1e-6)
+    assert torch.allclose(g, ref * (0.05 / ref.abs().max()), rtol=1e-6)
+    # AdamUniform.step (utils/optimizer.py:37-89) restated in torch vs the two-launch CUDA version
+    n = 5000
+    p = torch.randn(n, 3, device="cuda")
+    p_ref, g1r, g2r = p.clone(), torch.zeros_like(p), torch.zeros_like(p)
+    g1, g2, work = torch.zeros_like(p), torch.zeros_like(p), torch.zeros(4, device="cuda")
+    lr, b1, b2, limit = 0.2, 0.9, 0.999, 0.01
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 6):
+        grad = torch.randn(n, 3, device="cuda") * (0.1 if step != 3 else 10.0)
+        g1r.mul_(b1).add_(grad, alpha=1 - b1)
+        g2r.mul_(b2).add_(grad.square(), alpha=1 - b2)
+        m1, m2 = g1r / (1 - b1 ** step), g2r / (1 - b2 ** step)
+        gr = m1 / (1e-8 + m2.sqrt().max())
+        s = gr.abs().max()
+        if s > limit:
+            gr = gr * (limit / s)
+        p_ref.sub_(gr, alpha=lr)
+        rc = _capi.lib.tsb_adam_uniform_step(p.data_ptr(), grad.data_ptr(), g1.data_ptr(), g2.data_ptr(), p.numel(),
+                                             lr, b1, b2, step, limit, work.data_ptr(), st)
+        assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.allclose(p, p_ref, rtol=1e-5, atol=1e-7) and torch.allclose(g1, g1r, rtol=1e-6, atol=1e-9)
+    assert torch.all(work == 0)

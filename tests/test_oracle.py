@@ -1,0 +1,149 @@
+"""CPU tests of the oracle itself: known answers, golden fixtures, finite differences, agreement of
+the two independent restatements (numpy sparse-operator vs C matrix-free)."""
+import os
+
+import numpy as np
+import pytest
+
+from _helpers import GOLDEN, COracle
+from oracle.tet_energy_oracle import (ReferenceEnergyOracle, build_G, deformation_gradients, face_adjacency,
+                                      rest_inverse)
+from tssplat_b200.mesh import concat_spheres, make_tet_sphere, perturb
+
+
+@pytest.fixture(scope="module")
+def sphere():
+    v, t = make_tet_sphere(1003, 512)
+    return v.astype(np.float32).astype(np.float64), t
+
+
+@pytest.fixture(scope="module")
+def aveg():
+    d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
+    return d["verts"], d["tets"]
+
+
+def test_fixture_mesh_matches_survey(aveg):
+    v, t = aveg
+    assert v.shape == (4500, 3) and t.shape == (22120, 4)          # tssplat_ext/a.veg:2
+    nbr = face_adjacency(t)
+    assert np.bincount((nbr >= 0).sum(1), minlength=5).tolist() == [0, 0, 0, 1942, 20178]
+
+
+def test_known_answers_rest_affine_reflection(sphere):
+    v, t = sphere
+    for orc in (ReferenceEnergyOracle(v, t), COracle(v, t)):
+        def E(x, c1=1.0, c2=1.0, order=2):
+            if isinstance(orc, COracle):
+                return orc.energy_grad(x, c1, c2, order)[0]
+            return float(orc.forward(x, c1, c2, order))
+        assert abs(E(v)) < 1e-9                                     # rest: F = I
+        A = np.array([[1.1, 0.2, 0.0], [0.0, 0.9, 0.1], [0.1, 0.0, 1.2]])
+        xa = (v @ A.T + 0.3).astype(np.float32)
+        assert abs(E(xa)) < 1e-6 * len(t)                           # affine, det>0: L F = 0, no barrier
+        xr = (v * np.array([1, 1, -1])).astype(np.float32)          # reflection: det F = -1 everywhere
+        assert E(xr, 1.0, 1.0, 2) == pytest.approx(len(t), rel=1e-9)
+        assert E(xr, 1.0, 1.0, 4) == pytest.approx(len(t), rel=1e-9)
+        assert E(xr, 1.0, 0.25, 2) == pytest.approx(0.25 * len(t), rel=1e-9)
+
+
+def test_two_restatements_agree(sphere):
+    v, t = sphere
+    for scale in (0, 1):
+        o1, o2 = ReferenceEnergyOracle(v, t, laplacian_scale=scale), COracle(v, t, scale)
+        for sig, seed, order in ((0.02, 0, 2), (0.35, 1, 2), (0.35, 1, 4)):
+            x = perturb(v, t, sig, seed)
+            e2, terms, g2 = o2.energy_grad(x, 3e-4, 2e-4, order, gradH=0.7)
+            sm, bar = o1.energy_terms(x, order)
+            assert terms[0] == pytest.approx(float(sm), rel=1e-10)
+            assert terms[1] == pytest.approx(float(bar), rel=1e-10, abs=1e-300)
+            g1 = o1.backward(0.7, x, 3e-4, 2e-4, order)
+            assert np.linalg.norm(g1 - g2) <= 1e-10 * np.linalg.norm(g1)
+
+
+def test_G_matches_per_tet_definition(sphere):
+    """vec(F) = G x with F = Ds Dm^-1 (geometry/mesh_utils.py:38-69)."""
+    v, t = sphere
+    x = perturb(v, t, 0.2, 3).astype(np.float64)
+    F = deformation_gradients(x, t, rest_inverse(v, t))
+    Fg = (build_G(v, t) @ x.reshape(-1)).reshape(-1, 3, 3)
+    assert np.abs(F - Fg).max() < 1e-11
+
+
+def test_finite_differences(sphere):
+    v, t = sphere
+    orc = COracle(v, t)
+    rng = np.random.default_rng(5)
+    for sig, order in ((0.05, 2), (0.35, 2), (0.35, 4)):
+        x = perturb(v, t, sig, 2)
+        _, _, g = orc.energy_grad(x, 0.7, 1.3, order)
+        d = rng.normal(size=x.shape)
+        d /= np.linalg.norm(d)
+        h = 2.0 ** -9                       # exactly representable step keeps x +- h*d in float32 range
+        xp = (x.astype(np.float64) + h * d).astype(np.float32)
+        xm = (x.astype(np.float64) - h * d).astype(np.float32)
+        dd = (xp.astype(np.float64) - xm.astype(np.float64))         # the step actually taken
+        ep = orc.energy_grad(xp, 0.7, 1.3, order, want_grad=False)[0]
+        em = orc.energy_grad(xm, 0.7, 1.3, order, want_grad=False)[0]
+        assert ep - em == pytest.approx(float((g * dd).sum()), rel=2e-4)
+
+
+def test_block_diagonal_by_sphere():
+    """Energy/gradient of concatenated spheres = per-sphere values (the multi-GPU correctness basis)."""
+    sph = [make_tet_sphere(1100 + i, 256) for i in range(3)]
+    pack = concat_spheres([(v + 2.5 * i, t) for i, (v, t) in enumerate(sph)])
+    x = perturb(pack, sigma_rel=0.3, seed=4)
+    e_all, _, g_all = COracle(pack.verts, pack.tets).energy_grad(x, 0.5, 2.0, 2)
+    e_sum, gs = 0.0, []
+    for s in range(3):
+        sub = pack.slice_spheres(s, s + 1)
+        v0, v1 = pack.vert_offsets[s], pack.vert_offsets[s + 1]
+        e, _, g = COracle(sub.verts, sub.tets).energy_grad(x[v0:v1], 0.5, 2.0, 2)
+        e_sum += e
+        gs.append(g)
+    assert e_all == pytest.approx(e_sum, rel=1e-12)
+    assert np.abs(np.concatenate(gs) - g_all).max() < 1e-12 * max(1.0, np.abs(g_all).max())
+
+
+def test_order_other_than_2_or_4_gives_zero_barrier(sphere):
+    """tet_spheres_cuda.cu:57-63,83-89: silently zero."""
+    v, t = sphere
+    orc = ReferenceEnergyOracle(v, t)
+    x = perturb(v, t, 0.35, 1)
+    assert orc.energy_terms(x, 3)[1] == 0.0
+    g3 = orc.backward(1.0, x, 0.0, 1.0, 3)
+    assert np.all(g3 == 0.0)
+
+
+def test_fp32_mode_shows_reference_roundoff_floor(sphere):
+    """The reference evaluates 0.5 x^T (M x) in fp32 (tet_spheres_cuda.cu:131-157): near the rest
+    state that form cancels, so its own error is orders above 1e-5 -- which is why parity is judged
+    against the fp64 restatement."""
+    v, t = sphere
+    x = perturb(v, t, 0.02, 0)
+    e64 = float(ReferenceEnergyOracle(v, t).forward(x, 1.0, 1.0, 2))
+    e32 = float(ReferenceEnergyOracle(v, t, dtype=np.float32).forward(x, 1.0, 1.0, 2))
+    assert e32 == pytest.approx(e64, rel=0.2)
+    g64 = ReferenceEnergyOracle(v, t).backward(1.0, x, 1.0, 1.0, 2)
+    g32 = ReferenceEnergyOracle(v, t, dtype=np.float32).backward(1.0, x, 1.0, 1.0, 2)
+    assert np.linalg.norm(g32 - g64) < 1e-2 * np.linalg.norm(g64)
+
+
+def test_oracle_reproduces_golden(aveg):
+    gold = np.load(os.path.join(GOLDEN, "golden_energy.npz"))
+    from tssplat_b200.mesh import make_pack
+    meshes = {"a_veg": aveg}
+    pk = make_pack(3, 1024, seed=1)
+    meshes["pack3x1024"] = (pk.verts.astype(np.float64), pk.tets)
+    cases = {"benign_o2": (0.02, 0, 2, 2e-4, 2e-4, 1.0), "inverted_o2": (0.35, 1, 2, 3.2e-3, 3.2e-3, 0.5),
+             "inverted_o4": (0.35, 1, 4, 2e-4, 2e-4, 1.0)}
+    for mname, (v, t) in meshes.items():
+        orc = COracle(v, t)
+        for cname, (sig, seed, order, c1, c2, gh) in cases.items():
+            x = perturb(v, t, sig, seed)
+            e, terms, g = orc.energy_grad(x, c1, c2, order, gradH=gh)
+            k = f"{mname}/{cname}"
+            assert e == pytest.approx(float(gold[k + "/energy"]), rel=1e-10)
+            assert terms[0] == pytest.approx(float(gold[k + "/smooth"]), rel=1e-10)
+            assert np.linalg.norm(g) == pytest.approx(float(gold[k + "/grad_l2"]), rel=1e-10)
+            assert np.abs(g[:: max(1, len(g) // 64)][:64] - gold[k + "/grad_sample"]).max() <= 1e-9 * np.abs(g).max()
