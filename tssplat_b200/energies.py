@@ -56,7 +56,7 @@ class SmoothnessBarrierEnergy(torch.nn.Module):
         f_flat = np.asarray(tet_f).flatten().astype(np.int32)
         self.tet_sp = tet_spheres_ext.TetSpheres(v_flat, f_flat)
         self.FLAGS = SimpleNamespace(**FLAGS) if isinstance(FLAGS, dict) else FLAGS
-        self.smooth_eng_func = SmoothnessBarrierFunc()
+        self.smooth_eng_func = SmoothnessBarrierFunc          # the reference instantiates it; .apply is static
 
     def coeff_scheduler(self, it):
         """Both coefficients times ``2 ** (4 |sin(min(it/2400 * pi, pi/2))|)`` in [1, 16]
