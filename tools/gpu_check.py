@@ -33,10 +33,11 @@ def parity(pack, tile_tets, sig, order, scale=0):
           f"nan={int(np.isnan(gg).sum())} deterministic={det} tiles={sp.info['n_tiles']}")
 
 
-def timing(pack, tile_tets, threads512=256, reps=200):
+def timing(pack, tile_tets, threads512=256, reps=200, skip_combine=0):
     import ctypes
     from tssplat_b200 import _capi
     _capi.lib.tsb_debug_set_threads_512(ctypes.c_int(threads512))
+    _capi.lib.tsb_debug_set_skip_combine(ctypes.c_int(skip_combine))
     sp = ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1), tile_tets=tile_tets)
     x = torch.from_numpy(perturb(pack, sigma_rel=0.02, seed=0)).cuda()
     c1, c2 = 2e-4 / pack.num_spheres, 2e-4
@@ -69,7 +70,8 @@ def timing(pack, tile_tets, threads512=256, reps=200):
     s.record(); g.replay(); e.record(); torch.cuda.synchronize()
     t_graph = s.elapsed_time(e) / reps * 1e3
     balg = pack.algorithmic_bytes()
-    print(f"  S={pack.num_spheres} TT={tile_tets} NT512={threads512}: eager {t_eager:.2f} us/launch, graph {t_graph:.2f} us/launch "
+    _capi.lib.tsb_debug_set_skip_combine(ctypes.c_int(0))
+    print(f"  S={pack.num_spheres} TT={tile_tets} NT512={threads512} skip_combine={skip_combine}: eager {t_eager:.2f} us/launch, graph {t_graph:.2f} us/launch "
           f"(warm L2), B_alg={balg/1e6:.1f} MB -> {balg/t_graph/1e3:.0f} GB/s; tiles={sp.info['n_tiles']} "
           f"stream_bytes={sp.info['stream_bytes']/1e6:.1f} MB dup={sp.info['n_local_vertices']/sp.n:.2f}")
 
@@ -85,5 +87,8 @@ if __name__ == "__main__":
     parity(small, 512, 0.35, 2, scale=1)
     t0 = time.time(); pack = make_pack(S, T, seed=0, unique=8); print(f"pack S={S} T={T}: n={pack.n} nele={pack.nele} ({time.time()-t0:.1f}s)")
     parity(pack, 512, 0.35, 2)
+    if os.environ.get("QUICK"):
+        timing(pack, 512, 256); timing(pack, 512, 256, skip_combine=1); timing(pack, 256, 256); timing(pack, 256, 256, skip_combine=1)
+        sys.exit(0)
     for tt, nt in ((256, 256), (512, 256), (512, 512), (1024, 512)):
         timing(pack, tt, nt)

@@ -262,5 +262,6 @@ void tsb_debug_set_timing(tsb_handle_t h, long long *dbg_dev) { if (h) h->kp.dbg
 
 /* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
 void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
+void tsb_debug_set_skip_combine(int v) { tsb::set_skip_combine(v); }
 
 }  // extern "C"

@@ -79,6 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+int g_skip_combine = 0;   // developer switch (timing experiments only)
 
 __device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
@@ -369,9 +370,14 @@ __global__ void __launch_bounds__(NT) combine_kernel(const __grid_constant__ KPa
   if (v < n_vertices) {
     const float4 *scratch4 = reinterpret_cast<const float4 *>(p.scratch);
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    for (int s = s0; s < s1; ++s) {
-      const float4 q = __ldcg(scratch4 + s);
-      g0 += q.x; g1 += q.y; g2 += q.z;
+    // slots are summed in index order (deterministic); loads are issued 4 at a time so the L2 round
+    // trips overlap instead of forming a dependent chain
+    for (int s = s0; s < s1; s += 4) {
+      float4 q[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = (s + j < s1) ? __ldcg(scratch4 + s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { g0 += q[j].x; g1 += q[j].y; g2 += q[j].z; }
     }
     float *gp = p.grad + 3 * size_t(v);
     gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
@@ -480,7 +486,7 @@ cudaError_t launch_variant(const KParams &p, int n_vertices, const int32_t *slot
   if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
   else energy_grad_kernel<TT, NV, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || g_skip_combine) return e;
   // combine kernel, chained with programmatic dependent launch
   constexpr int CNT = 256;
   const int nv = p.grad ? n_vertices : 0;
@@ -546,6 +552,7 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 }
 
 void set_threads_512(int nt) { g_threads_512 = (nt == 512) ? 512 : 256; }
+void set_skip_combine(int v) { g_skip_combine = v; }
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s) {
   scale_kernel<<<grid_for(count, 256), 256, 0, s>>>(g, count, gradH, gradH_dev, out);

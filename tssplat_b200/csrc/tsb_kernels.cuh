@@ -35,6 +35,7 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 cudaError_t prepare_energy_grad(int tile_tets);
 int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
 void set_threads_512(int nt);
+void set_skip_combine(int v);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);
 cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st);

@@ -160,43 +160,100 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   std::iota(P.tet_order.begin(), P.tet_order.end(), 0);
   std::stable_sort(P.tet_order.begin(), P.tet_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
 
-  // ---- tiling: `fill` tets per tile (wave-balanced), closed early if NVMAX vertices are reached ---
-  int fill = TT;
-  if (opt.balance_sms > 0) {
-    const int64_t per_round = int64_t(opt.balance_sms) * TT;
-    const int64_t rounds = (int64_t(nele) + per_round - 1) / per_round;
-    const int64_t tiles = rounds * opt.balance_sms;
-    fill = int((int64_t(nele) + tiles - 1) / tiles);
-    fill = std::min(TT, std::max(TT / 4, ((fill + 7) / 8) * 8));
-  }
-  P.fill = fill;
+  // ---- tiling: recursive coordinate bisection inside each component ----------------------------
+  // The tile count is matched to the SM count (a whole number of waves), tiles are distributed over
+  // components in proportion to their tet counts, and each component is split into boxy parts of
+  // (almost) equal size; inside a tile tets keep the Morton order (locality of the warp's gathers).
+  // A tile that would stage more than NVMAX vertices makes its component use one more tile.
   {
+    // component -> [begin, end) in tet_order (tet_order is sorted by component first)
+    std::vector<int32_t> comp_begin(size_t(NC) + 1, 0);
+    for (int t = 0; t < nele; ++t) comp_begin[size_t(key[t] >> 32) + 1]++;
+    for (int c = 0; c < NC; ++c) comp_begin[size_t(c) + 1] += comp_begin[c];
+    int64_t target = (int64_t(nele) + TT - 1) / TT;
+    if (opt.balance_sms > 0) {
+      const int64_t per_round = int64_t(opt.balance_sms) * TT;
+      const int64_t rounds = (int64_t(nele) + per_round - 1) / per_round;
+      // do not go below a quarter-full tile: tiny meshes keep a handful of tiles
+      target = std::min<int64_t>(rounds * opt.balance_sms, std::max<int64_t>(target, (int64_t(nele) + TT / 4 - 1) / (TT / 4)));
+    }
+    std::vector<float> cen(size_t(nele) * 3);
+    for (int t = 0; t < nele; ++t) {
+      const int32_t *v = tets + 4 * size_t(t);
+      for (int r = 0; r < 3; ++r)
+        cen[3 * size_t(t) + r] = 0.25f * (rest[3 * size_t(v[0]) + r] + rest[3 * size_t(v[1]) + r] + rest[3 * size_t(v[2]) + r] + rest[3 * size_t(v[3]) + r]);
+    }
     std::vector<int32_t> stamp(n, -1);
-    int cur_tets = 0, cur_verts = 0, tile = 0;
-    P.tile_first.push_back(0);
-    for (int pos = 0; pos < nele; ++pos) {
-      const int t = P.tet_order[pos];
-      int32_t st[8];
-      for (int k = 0; k < 4; ++k) { st[k] = tets[4 * size_t(t) + k]; st[4 + k] = opp[4 * size_t(t) + k]; }
-      auto count_new = [&](int tl) {
-        int add = 0;
-        for (int k = 0; k < 8; ++k) {
-          if (st[k] < 0 || stamp[st[k]] == tl) continue;
-          bool dup = false;
-          for (int j = 0; j < k; ++j) dup |= (st[j] == st[k]);
-          add += !dup;
+    int stamp_id = 0;
+    auto staged_vertices = [&](const int32_t *first, const int32_t *last) {
+      ++stamp_id;
+      int cnt = 0;
+      for (const int32_t *it = first; it != last; ++it)
+        for (int k = 0; k < 4; ++k) {
+          const int32_t a0 = tets[4 * size_t(*it) + k], a1 = opp[4 * size_t(*it) + k];
+          if (stamp[a0] != stamp_id) { stamp[a0] = stamp_id; ++cnt; }
+          if (a1 >= 0 && stamp[a1] != stamp_id) { stamp[a1] = stamp_id; ++cnt; }
         }
-        return add;
-      };
-      int add = count_new(tile);
-      if (cur_tets == fill || cur_verts + add > NVMAX) {
-        ++tile; P.tile_first.push_back(pos); cur_tets = 0; cur_verts = 0;
-        add = count_new(tile);
+      return cnt;
+    };
+    std::vector<int32_t> work;          // tets of one component, permuted in place by the bisection
+    std::vector<std::pair<int32_t, int32_t>> parts;   // [begin,end) in `work`
+    struct Job { int32_t b, e, k; };
+    std::vector<Job> stack;
+    std::vector<int32_t> new_order;
+    new_order.reserve(nele);
+    P.tile_first.clear();
+    int max_fill = 0;
+    for (int c = 0; c < NC; ++c) {
+      const int cb = comp_begin[c], ce = comp_begin[size_t(c) + 1], nt = ce - cb;
+      int k = int(std::max<int64_t>((nt + TT - 1) / TT, (int64_t(nt) * target + nele / 2) / nele));
+      k = std::max(1, std::min(k, nt));
+      for (;;) {
+        work.assign(P.tet_order.begin() + cb, P.tet_order.begin() + ce);
+        parts.clear();
+        stack.clear();
+        stack.push_back(Job{0, nt, k});
+        while (!stack.empty()) {
+          const Job j = stack.back();
+          stack.pop_back();
+          if (j.k == 1) { parts.emplace_back(j.b, j.e); continue; }
+          float lo3[3] = {3e38f, 3e38f, 3e38f}, hi3[3] = {-3e38f, -3e38f, -3e38f};
+          for (int i = j.b; i < j.e; ++i)
+            for (int r = 0; r < 3; ++r) {
+              lo3[r] = std::min(lo3[r], cen[3 * size_t(work[i]) + r]);
+              hi3[r] = std::max(hi3[r], cen[3 * size_t(work[i]) + r]);
+            }
+          int ax = 0;
+          for (int r = 1; r < 3; ++r) if (hi3[r] - lo3[r] > hi3[ax] - lo3[ax]) ax = r;
+          const int k1 = j.k / 2, k2 = j.k - k1;
+          const int n1 = int((int64_t(j.e - j.b) * k1 + j.k / 2) / j.k);
+          std::nth_element(work.begin() + j.b, work.begin() + j.b + n1, work.begin() + j.e, [&](int32_t a, int32_t b2) {
+            const float ca = cen[3 * size_t(a) + ax], cb2 = cen[3 * size_t(b2) + ax];
+            return ca < cb2 || (ca == cb2 && a < b2);
+          });
+          stack.push_back(Job{j.b + n1, j.e, k2});
+          stack.push_back(Job{j.b, j.b + n1, k1});
+        }
+        bool ok = true;
+        for (const auto &pr : parts) {
+          if (pr.second - pr.first > TT) { ok = false; break; }
+          if (staged_vertices(work.data() + pr.first, work.data() + pr.second) > NVMAX) { ok = false; break; }
+        }
+        if (ok || k >= nt) break;
+        k = std::min(nt, k + std::max(1, k / 8));
       }
-      for (int k = 0; k < 8; ++k) if (st[k] >= 0) stamp[st[k]] = tile;
-      cur_tets += 1; cur_verts += add;
+      std::sort(parts.begin(), parts.end());
+      for (const auto &pr : parts) {
+        if (pr.second == pr.first) continue;
+        std::sort(work.begin() + pr.first, work.begin() + pr.second, [&](int32_t a, int32_t b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
+        P.tile_first.push_back(int32_t(new_order.size()));
+        new_order.insert(new_order.end(), work.begin() + pr.first, work.begin() + pr.second);
+        max_fill = std::max(max_fill, pr.second - pr.first);
+      }
     }
     P.tile_first.push_back(nele);
+    P.tet_order.swap(new_order);
+    P.fill = std::min(TT, ((max_fill + 7) / 8) * 8);
   }
   const int NTILE = int(P.tile_first.size()) - 1;
   P.n_tiles = NTILE;
