@@ -86,6 +86,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     if (opt->tile_tets != 0) po.tile_tets = opt->tile_tets;
     po.laplacian_scale = opt->laplacian_scale ? 1 : 0;
   }
+  if (const char *env = std::getenv("TSSPLAT_B200_V4")) tsb::set_use_v4(std::atoi(env));
   if (const char *env = std::getenv("TSSPLAT_B200_TILE_TETS")) {
     if (!(opt && opt->tile_tets != 0)) po.tile_tets = std::atoi(env);
   }
@@ -117,6 +118,11 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   TSB_TRY(upload(h, plan.tblob, &kp.tblob, 16));
   TSB_TRY(upload(h, plan.ell, &kp.ell, 8));
   TSB_TRY(upload(h, plan.slot_ptr, &h->slot_ptr, 2));
+  {
+    const int32_t *te = nullptr;
+    TSB_TRY(upload(h, plan.tile_ell, &te, 2));
+    kp.tile_ell = reinterpret_cast<const int2 *>(te);
+  }
   TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 4, &kp.scratch));
   TSB_TRY(alloc_zero(h, size_t(plan.n_tiles) * 2, &kp.tile_energy));
 #undef TSB_TRY
@@ -241,7 +247,7 @@ int tsb_debug_plan_array(tsb_debug_plan_s *d, const char *name, const void **ptr
   const std::string k(name);
 #define TSB_ARR(nm, vec) if (k == nm) { *ptr = (vec).data(); *count = int64_t((vec).size()); *elem_bytes = int32_t(sizeof((vec)[0])); return TSB_OK; }
   TSB_ARR("vblob", P.vblob) TSB_ARR("tblob", P.tblob) TSB_ARR("ell", P.ell) TSB_ARR("slot_ptr", P.slot_ptr)
-  TSB_ARR("tet_order", P.tet_order) TSB_ARR("tile_first", P.tile_first)
+  TSB_ARR("tet_order", P.tet_order) TSB_ARR("tile_first", P.tile_first) TSB_ARR("tile_ell", P.tile_ell)
 #undef TSB_ARR
   return TSB_E_INVALID;
 }
@@ -263,5 +269,6 @@ void tsb_debug_set_timing(tsb_handle_t h, long long *dbg_dev) { if (h) h->kp.dbg
 /* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
 void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
 void tsb_debug_set_skip_combine(int v) { tsb::set_skip_combine(v); }
+void tsb_debug_set_use_v4(int v) { tsb::set_use_v4(v); }
 
 }  // extern "C"

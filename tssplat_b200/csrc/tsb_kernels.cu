@@ -112,6 +112,138 @@ __device__ __forceinline__ void gather_vertex(const float *outb, const uint32_t 
   }
 }
 
+// One tet: 13 shared-memory gathers, barrier + smoothness energy terms, and (WITH_GRAD) its 8 output
+// 3-vectors written to column `lt` of the [24][TTP] table.  Shared by both tile kernels.
+template <int TTP, bool WITH_GRAD>
+__device__ __forceinline__ void tet_body(const int lt, const uint4 *__restrict__ idx_s, const float *__restrict__ B_s,
+                                         const float4 *__restrict__ xs4, const float2 *__restrict__ xs2,
+                                         float *__restrict__ outb, const float c1, const float c2, const int order,
+                                         const bool lscale, float &es, float &eb) {
+  const uint4 iv = idx_s[lt];
+  float b[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) b[i] = B_s[lt * 9 + i];
+  const unsigned iown[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
+  const unsigned ioppr[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
+
+  const float4 p0 = xs4[iown[0]];
+  const float2 q0 = xs2[iown[0]];
+  float e[3][3];  // e[j][r] = x_{v_{j+1}}[r] - x_{v0}[r]
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float4 pj = xs4[iown[j + 1]];
+    e[j][0] = pj.x - p0.x; e[j][1] = pj.y - p0.y; e[j][2] = pj.z - p0.z;
+  }
+  float4 po[4];
+  float2 qo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { po[k] = xs4[ioppr[k] & 0x7fffu]; qo[k] = xs2[ioppr[k] & 0x7fffu]; }
+
+  // hat gradients: a[0] = -(a1+a2+a3), a[j] = row j-1 of B
+  float a[4][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    a[1][c] = b[c]; a[2][c] = b[3 + c]; a[3][c] = b[6 + c];
+    a[0][c] = -(b[c] + b[3 + c] + b[6 + c]);
+  }
+
+  float z[3][3];  // gradient contributions to own vertices 1..3 (vertex 0 follows from momentum)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
+  {
+    float F[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) F[r][c] = e[0][r] * a[1][c] + e[1][r] * a[2][c] + e[2][r] * a[3][c];
+    // cofactors = d det / dF  (tet_spheres_cuda.cu:32-46)
+    const float C00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
+    const float C01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
+    const float C02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
+    const float J = F[0][0] * C00 + F[0][1] * C01 + F[0][2] * C02;
+    if (J < 0.f) {   // rare: inverted tet
+      const float m = -J;
+      float coef;
+      if (order == 2) { eb += m * m; coef = 2.f * m; }
+      else { const float m2 = m * m; eb += m2 * m2; coef = 4.f * m2 * m; }
+      if (WITH_GRAD) {
+        float C[3][3];
+        C[0][0] = C00; C[0][1] = C01; C[0][2] = C02;
+        C[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
+        C[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0];
+        C[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
+        C[2][0] = F[0][1] * F[1][2] - F[0][2] * F[1][1];
+        C[2][1] = F[0][2] * F[1][0] - F[0][0] * F[1][2];
+        C[2][2] = F[0][0] * F[1][1] - F[0][1] * F[1][0];
+        const float pc = -c2 * coef;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float P0 = pc * C[r][0], P1 = pc * C[r][1], P2 = pc * C[r][2];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) z[j][r] = P0 * a[j + 1][0] + P1 * a[j + 1][1] + P2 * a[j + 1][2];
+        }
+      }
+    }
+  }
+
+  // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k      (branch-free; boundary faces have
+  // rho = 0 and gather the tet's own vertex)
+  float H[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { H[r][0] = 0.f; H[r][1] = 0.f; H[r][2] = 0.f; }
+  float lam[4][3], rho[4];
+  int deg = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool valid = (ioppr[k] & 0x8000u) != 0u;
+    deg += valid ? 1 : 0;
+    const float rx = po[k].w - p0.w, ry = qo[k].x - q0.x, rz = qo[k].y - q0.y;
+    const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
+    const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
+    const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
+    const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
+    const float rk = valid ? __fdividef(-1.f, lkk) : 0.f;
+    lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
+    const float dx = (po[k].x - p0.x) - l1 * e[0][0] - l2 * e[1][0] - l3 * e[2][0];
+    const float dy = (po[k].y - p0.y) - l1 * e[0][1] - l2 * e[1][1] - l3 * e[2][1];
+    const float dz = (po[k].z - p0.z) - l1 * e[0][2] - l2 * e[1][2] - l3 * e[2][2];
+    const float sx = rk * dx, sy = rk * dy, sz = rk * dz;
+    H[0][0] += sx * a[k][0]; H[0][1] += sx * a[k][1]; H[0][2] += sx * a[k][2];
+    H[1][0] += sy * a[k][0]; H[1][1] += sy * a[k][1]; H[1][2] += sy * a[k][2];
+    H[2][0] += sz * a[k][0]; H[2][1] += sz * a[k][1]; H[2][2] += sz * a[k][2];
+  }
+  const float w = (lscale && deg > 0) ? __fdividef(1.f, float(deg)) : 1.f;
+  float hh = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { H[r][c] *= w; hh += H[r][c] * H[r][c]; }
+  es += 0.5f * hh;
+
+  if (WITH_GRAD) {
+    const float cw = c1 * w;
+    float ys[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float sk = cw * rho[k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
+        outb[((4 + k) * 3 + r) * TTP + lt] = y;
+        ys[r] += y;
+        z[0][r] -= lam[k][0] * y; z[1][r] -= lam[k][1] * y; z[2][r] -= lam[k][2] * y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      outb[(0 * 3 + r) * TTP + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
+      outb[(1 * 3 + r) * TTP + lt] = z[0][r];
+      outb[(2 * 3 + r) * TTP + lt] = z[1][r];
+      outb[(3 * 3 + r) * TTP + lt] = z[2][r];
+    }
+  }
+}
+
 template <int TT, int NV, int NT, int MINB, bool WITH_GRAD>
 __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_constant__ KParams p) {
   using L = Smem<TT, NV>;
@@ -193,131 +325,8 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   const float c1 = p.c1, c2 = p.c2;
   const int order = p.order;
   const bool lscale = p.laplacian_scale != 0;
-  for (int lt = tid; lt < ntet; lt += NT) {
-    const uint4 iv = idx_s[lt];
-    float b[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) b[i] = B_s[lt * 9 + i];
-    const unsigned iown[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
-    const unsigned ioppr[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
-
-    const float4 p0 = xs4[iown[0]];
-    const float2 q0 = xs2[iown[0]];
-    float e[3][3];  // e[j][r] = x_{v_{j+1}}[r] - x_{v0}[r]
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float4 pj = xs4[iown[j + 1]];
-      e[j][0] = pj.x - p0.x; e[j][1] = pj.y - p0.y; e[j][2] = pj.z - p0.z;
-    }
-    float4 po[4];
-    float2 qo[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { po[k] = xs4[ioppr[k] & 0x7fffu]; qo[k] = xs2[ioppr[k] & 0x7fffu]; }
-
-    // hat gradients: a[0] = -(a1+a2+a3), a[j] = row j-1 of B
-    float a[4][3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      a[1][c] = b[c]; a[2][c] = b[3 + c]; a[3][c] = b[6 + c];
-      a[0][c] = -(b[c] + b[3 + c] + b[6 + c]);
-    }
-
-    float z[3][3];  // gradient contributions to own vertices 1..3 (vertex 0 follows from momentum)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
-    {
-      float F[3][3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) F[r][c] = e[0][r] * a[1][c] + e[1][r] * a[2][c] + e[2][r] * a[3][c];
-      // cofactors = d det / dF  (tet_spheres_cuda.cu:32-46)
-      const float C00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
-      const float C01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
-      const float C02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
-      const float J = F[0][0] * C00 + F[0][1] * C01 + F[0][2] * C02;
-      if (J < 0.f) {   // rare: inverted tet
-        const float m = -J;
-        float coef;
-        if (order == 2) { eb += m * m; coef = 2.f * m; }
-        else { const float m2 = m * m; eb += m2 * m2; coef = 4.f * m2 * m; }
-        if (WITH_GRAD) {
-          float C[3][3];
-          C[0][0] = C00; C[0][1] = C01; C[0][2] = C02;
-          C[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
-          C[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0];
-          C[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
-          C[2][0] = F[0][1] * F[1][2] - F[0][2] * F[1][1];
-          C[2][1] = F[0][2] * F[1][0] - F[0][0] * F[1][2];
-          C[2][2] = F[0][0] * F[1][1] - F[0][1] * F[1][0];
-          const float pc = -c2 * coef;
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const float P0 = pc * C[r][0], P1 = pc * C[r][1], P2 = pc * C[r][2];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) z[j][r] = P0 * a[j + 1][0] + P1 * a[j + 1][1] + P2 * a[j + 1][2];
-          }
-        }
-      }
-    }
-
-    // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k      (branch-free; boundary faces have
-    // rho = 0 and gather the tet's own vertex)
-    float H[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) { H[r][0] = 0.f; H[r][1] = 0.f; H[r][2] = 0.f; }
-    float lam[4][3], rho[4];
-    int deg = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool valid = (ioppr[k] & 0x8000u) != 0u;
-      deg += valid ? 1 : 0;
-      const float rx = po[k].w - p0.w, ry = qo[k].x - q0.x, rz = qo[k].y - q0.y;
-      const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
-      const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
-      const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
-      const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
-      const float rk = valid ? __fdividef(-1.f, lkk) : 0.f;
-      lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
-      const float dx = (po[k].x - p0.x) - l1 * e[0][0] - l2 * e[1][0] - l3 * e[2][0];
-      const float dy = (po[k].y - p0.y) - l1 * e[0][1] - l2 * e[1][1] - l3 * e[2][1];
-      const float dz = (po[k].z - p0.z) - l1 * e[0][2] - l2 * e[1][2] - l3 * e[2][2];
-      const float sx = rk * dx, sy = rk * dy, sz = rk * dz;
-      H[0][0] += sx * a[k][0]; H[0][1] += sx * a[k][1]; H[0][2] += sx * a[k][2];
-      H[1][0] += sy * a[k][0]; H[1][1] += sy * a[k][1]; H[1][2] += sy * a[k][2];
-      H[2][0] += sz * a[k][0]; H[2][1] += sz * a[k][1]; H[2][2] += sz * a[k][2];
-    }
-    const float w = (lscale && deg > 0) ? __fdividef(1.f, float(deg)) : 1.f;
-    float hh = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { H[r][c] *= w; hh += H[r][c] * H[r][c]; }
-    es += 0.5f * hh;
-
-    if (WITH_GRAD) {
-      const float cw = c1 * w;
-      float ys[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float sk = cw * rho[k];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
-          outb[((4 + k) * 3 + r) * TTP + lt] = y;
-          ys[r] += y;
-          z[0][r] -= lam[k][0] * y; z[1][r] -= lam[k][1] * y; z[2][r] -= lam[k][2] * y;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        outb[(0 * 3 + r) * TTP + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
-        outb[(1 * 3 + r) * TTP + lt] = z[0][r];
-        outb[(2 * 3 + r) * TTP + lt] = z[1][r];
-        outb[(3 * 3 + r) * TTP + lt] = z[2][r];
-      }
-    }
-  }
+  for (int lt = tid; lt < ntet; lt += NT)
+    tet_body<TTP, WITH_GRAD>(lt, idx_s, B_s, xs4, xs2, outb, c1, c2, order, lscale, es, eb);
 
   TSB_STAMP(6);
   // per-tile energy partials (tree reduction; the cross-tile sum is done in fp64 below)
@@ -355,6 +364,181 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   if (p.dbg && tid == 0) p.dbg[size_t(tile) * 16 + 15] = gtime_ns();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pipelined tile kernel: one persistent CTA per SM, 24 warps with fixed roles, a two-stage shared
+// memory ring per CTA, everything synchronised with mbarriers (no CTA-wide barrier in the loop).
+//   warps 0..15  compute : phase 1 (tet math) of tile k, one tet per thread, back to back
+//   warp  16     producer: TMA bulk copies of tile k+1 / k+2 blobs as soon as a stage is free
+//   warps 17..23 aux     : x gather of tile k+1 (global -> smem) and row gather of tile k (smem ->
+//                          scratch) while the compute warps are busy with the tet math
+// Why: with one tile per CTA the three phases run in lock-step on all resident CTAs, so the
+// latency-bound phases (0 and 2) cannot hide behind the issue-bound phase 1
+// (profiles/r01_summary.md: 9.9k cycles per tile of which phase 1 is 4.6k).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPipeComputeWarps = 16, kPipeAuxWarps = 7;
+constexpr int kPipeThreads = (kPipeComputeWarps + 1 + kPipeAuxWarps) * 32;   // 768
+
+template <int TT, int NV>
+struct PipeSmem {
+  static constexpr int NR = NV + 8 * TT / kRowCap;
+  static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;
+  static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
+  static constexpr int kTTP = TT + 4;
+  static constexpr int kVOff = 0;
+  static constexpr int kTOff = align_up(kVOff + kVBytes, 128);
+  static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
+  static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
+  static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
+  static constexpr int kStageBytes = align_up(kOutOff + 96 * kTTP, 128);
+  static constexpr int kBytes = 2 * kStageBytes;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps (error to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_guard(uint64_t *bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();
+  } while (!ok);
+}
+
+template <int TT, int NV, bool WITH_GRAD>
+__global__ void __launch_bounds__(kPipeThreads, 1) energy_grad_pipe_kernel(const __grid_constant__ KParams p) {
+  using L = PipeSmem<TT, NV>;
+  constexpr int NR = L::NR, TTP = L::kTTP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_v[2], bar_t[2], bar_e[2], bar_x[2], bar_out[2], bar_free[2];
+  __shared__ float s_red[2 * kPipeComputeWarps];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles b, b+G, b+2G, ...
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_v[s], 1); mbar_init(&bar_t[s], 1); mbar_init(&bar_e[s], 1);
+      mbar_init(&bar_x[s], kPipeAuxWarps); mbar_init(&bar_out[s], kPipeComputeWarps); mbar_init(&bar_free[s], kPipeAuxWarps);
+    }
+    mbar_fence_init();
+  }
+  if (WITH_GRAD && tid < 6) {   // zero columns of both stages' output tables (gather-table padding target)
+    float *ob = reinterpret_cast<float *>(smem_raw + (tid / 3) * L::kStageBytes + L::kOutOff);
+    ob[(tid % 3) * TTP + TT] = 0.f;
+  }
+  __syncthreads();
+
+  if (warp < kPipeComputeWarps) {
+    // ======================= compute warps: phase 1 ===============================================
+    float es = 0.f, eb = 0.f;
+    const float c1 = p.c1, c2 = p.c2;
+    const int order = p.order;
+    const bool lscale = p.laplacian_scale != 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int s = k & 1;
+      const uint32_t par = (k >> 1) & 1;
+      unsigned char *st = smem_raw + s * L::kStageBytes;
+      mbar_wait_guard(&bar_x[s], par);      // x of this tile staged (implies the vertex blob landed)
+      mbar_wait_guard(&bar_t[s], par);      // tet blob landed
+      const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
+      const int ntet = hd->ntet;
+      if (tid < ntet)
+        tet_body<TTP, WITH_GRAD>(tid, reinterpret_cast<const uint4 *>(st + L::kTOff),
+                                 reinterpret_cast<const float *>(st + L::kTOff + 16 * TT),
+                                 reinterpret_cast<const float4 *>(st + L::kXs4Off),
+                                 reinterpret_cast<const float2 *>(st + L::kVOff + 64 + 8 * NV),
+                                 reinterpret_cast<float *>(st + L::kOutOff), c1, c2, order, lscale, es, eb);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_out[s]);
+    }
+    // one (smooth, barrier) partial per CTA
+    const float ws = warp_sum(es), wb = warp_sum(eb);
+    if (lane == 0) { s_red[warp] = ws; s_red[kPipeComputeWarps + warp] = wb; }
+    asm volatile("bar.sync 1, %0;" ::"n"(kPipeComputeWarps * 32) : "memory");
+    if (warp == 0) {
+      float vs = (lane < kPipeComputeWarps) ? s_red[lane] : 0.f, vb = (lane < kPipeComputeWarps) ? s_red[kPipeComputeWarps + lane] : 0.f;
+      vs = warp_sum(vs); vb = warp_sum(vb);
+      if (lane == 0) { p.tile_energy[2 * blockIdx.x] = vs; p.tile_energy[2 * blockIdx.x + 1] = vb; }
+    }
+  } else if (warp == kPipeComputeWarps) {
+    // ======================= producer: TMA staging ================================================
+    if (lane == 0) {
+      const uint32_t nt_b = uint32_t(p.fill);
+      for (int k = 0; k < n_my; ++k) {
+        const int s = k & 1;
+        const int tile = int(blockIdx.x) + k * int(gridDim.x);
+        unsigned char *st = smem_raw + s * L::kStageBytes;
+        const int2 el = __ldg(p.tile_ell + tile);
+        if (k >= 2) mbar_wait_guard(&bar_free[s], ((k >> 1) - 1) & 1);   // previous tile in this stage fully consumed
+        mbar_expect_tx(&bar_v[s], L::kVBytes);
+        bulk_g2s(st + L::kVOff, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[s]);
+        mbar_expect_tx(&bar_t[s], 52u * nt_b);
+        const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
+        bulk_g2s(st + L::kTOff, tb, 16u * nt_b, &bar_t[s]);
+        bulk_g2s(st + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t[s]);
+        if (WITH_GRAD) {
+          mbar_expect_tx(&bar_e[s], 2u * uint32_t(el.y));
+          if (el.y > 0) bulk_g2s(st + L::kEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e[s]);
+        }
+      }
+    }
+  } else {
+    // ======================= aux warps: x gather (tile k+1) and row gather (tile k) ===============
+    constexpr int NA = kPipeAuxWarps * 32;
+    const int atid = tid - (kPipeComputeWarps + 1) * 32;
+    auto stage_x = [&](int k) {
+      const int s = k & 1;
+      const uint32_t par = (k >> 1) & 1;
+      unsigned char *st = smem_raw + s * L::kStageBytes;
+      mbar_wait_guard(&bar_v[s], par);
+      const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
+      const int32_t *vlist_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64);
+      const float *Xx_s = reinterpret_cast<const float *>(st + L::kVOff + 64 + 4 * NV);
+      float4 *xs4 = reinterpret_cast<float4 *>(st + L::kXs4Off);
+      const int nvert = hd->nvert;
+      for (int i = atid; i < nvert; i += NA) {
+        const float *xp = p.x + 3 * size_t(vlist_s[i]);
+        xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_x[s]);
+    };
+    if (n_my > 0) stage_x(0);
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) stage_x(k + 1);
+      const int s = k & 1;
+      const uint32_t par = (k >> 1) & 1;
+      unsigned char *st = smem_raw + s * L::kStageBytes;
+      mbar_wait_guard(&bar_out[s], par);           // compute warps finished this tile's table
+      if (WITH_GRAD) {
+        mbar_wait_guard(&bar_e[s], par);
+        const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
+        const int32_t *slot_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64 + 16 * NV);
+        const int32_t *grp_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64 + 16 * NV + 4 * NR);
+        const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(st + L::kEllOff);
+        const float *outb = reinterpret_cast<const float *>(st + L::kOutOff);
+        float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
+        const int nrow = hd->nrow;
+        for (int r = atid; r < nrow; r += NA) {
+          const int g = r >> 5, ln = r & 31;
+          const int beg = grp_s[g], end = grp_s[g + 1];
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+          gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + ln, (end - beg) >> 6, g0, g1, g2);
+          scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_free[s]);    // vertex blob, tet blob, table, gather table: all reusable
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Combine kernel: grad[v] = gradH * sum of v's scratch slots (fixed order); block 0 also folds the
 // per-tile energies in fp64.  Launched with programmatic stream serialization right behind the
 // tile kernel; griddepcontrol.wait blocks until that grid has completed and flushed.
@@ -384,7 +568,7 @@ __global__ void __launch_bounds__(NT) combine_kernel(const __grid_constant__ KPa
   }
   if (blockIdx.x == 0) {
     double as = 0.0, ab = 0.0;
-    for (int t = tid; t < p.n_tiles; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
+    for (int t = tid; t < p.n_energy; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
     as = warp_sum(as); ab = warp_sum(ab);
     __shared__ double s_dred[2 * (NT / 32)];
     if ((tid & 31) == 0) { s_dred[tid >> 5] = as; s_dred[NT / 32 + (tid >> 5)] = ab; }
@@ -480,14 +664,36 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
 #define TSB_V512 512, 384
 #define TSB_V1024 1024, 640
 
+cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
+int g_num_sms = 148;
+
+template <int TT, int NV>
+cudaError_t launch_pipe(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
+  KParams p = p0;
+  const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
+  p.n_energy = grid;
+  const int smem = PipeSmem<TT, NV>::kBytes;
+  if (p.grad) energy_grad_pipe_kernel<TT, NV, true><<<grid, kPipeThreads, smem, stream>>>(p);
+  else energy_grad_pipe_kernel<TT, NV, false><<<grid, kPipeThreads, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || g_skip_combine) return e;
+  return launch_combine(p, n_vertices, slot_ptr, stream);
+}
+
 template <int TT, int NV, int NT, int MINB>
-cudaError_t launch_variant(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
+cudaError_t launch_variant(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
+  KParams p = p0;
+  p.n_energy = p.n_tiles;
   const int smem = Smem<TT, NV>::kBytes;
   if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
   else energy_grad_kernel<TT, NV, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || g_skip_combine) return e;
-  // combine kernel, chained with programmatic dependent launch
+  return launch_combine(p, n_vertices, slot_ptr, stream);
+}
+
+// combine kernel, chained with programmatic dependent launch
+cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   constexpr int CNT = 256;
   const int nv = p.grad ? n_vertices : 0;
   cudaLaunchConfig_t cfg{};
@@ -518,10 +724,14 @@ inline int grid_for(int64_t count, int block) {
 
 }  // namespace
 
+static int g_use_v4 = 0;
+void set_use_v4(int v) { g_use_v4 = v; }
+int get_use_v4() { return g_use_v4; }
+
 int nvmax_for(int tile_tets) {
   switch (tile_tets) {
     case 256: return 256;
-    case 512: return 384;
+    case 512: return g_use_v4 ? 384 : 256;   // pipelined kernel stages 2 tiles -> smaller vertex capacity
     case 1024: return 640;
   }
   return 0;
@@ -533,9 +743,16 @@ cudaError_t prepare_energy_grad(int tile_tets) {
   switch (tile_tets) {
     case 256: return prepare_variant<TSB_V256, 256, 3>();
     case 512: {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
       cudaError_t e = prepare_variant<TSB_V512, 256, 2>();
       if (e != cudaSuccess) return e;
-      return prepare_variant<TSB_V512, 512, 1>();
+      e = prepare_variant<TSB_V512, 512, 1>();
+      if (e != cudaSuccess) return e;
+      const int smem = PipeSmem<512, 256>::kBytes;
+      e = cudaFuncSetAttribute(energy_grad_pipe_kernel<512, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(energy_grad_pipe_kernel<512, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }
     case 1024: return prepare_variant<TSB_V1024, 512, 1>();
   }
@@ -545,7 +762,9 @@ cudaError_t prepare_energy_grad(int tile_tets) {
 cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   switch (tile_tets) {
     case 256: return launch_variant<TSB_V256, 256, 3>(p, n_vertices, slot_ptr, stream);
-    case 512: return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, n_vertices, slot_ptr, stream) : launch_variant<TSB_V512, 256, 2>(p, n_vertices, slot_ptr, stream);
+    case 512:
+      if (!g_use_v4) return launch_pipe<512, 256>(p, n_vertices, slot_ptr, stream);
+      return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, n_vertices, slot_ptr, stream) : launch_variant<TSB_V512, 256, 2>(p, n_vertices, slot_ptr, stream);
     case 1024: return launch_variant<TSB_V1024, 512, 1>(p, n_vertices, slot_ptr, stream);
   }
   return cudaErrorInvalidValue;

@@ -13,9 +13,10 @@ struct KParams {
   const unsigned char *vblob;   // n_tiles * vblob_bytes(NV)
   const unsigned char *tblob;   // n_tiles * tblob_bytes(TT)
   const uint16_t *ell;          // gather tables
+  const int2 *tile_ell;         // (ell_off, nell) per tile
   // per-handle scratch
   float *scratch;               // [4*n_slots] per-(tile,vertex) partial gradients (float4)
-  float *tile_energy;           // [2*n_tiles] (smooth, barrier) per tile
+  float *tile_energy;           // [2*n_energy] (smooth, barrier) partials: per tile (v4) or per CTA (pipelined)
   // per launch
   const float *x;               // [3n]
   float *grad;                  // [3n] or nullptr (energy only)
@@ -25,6 +26,7 @@ struct KParams {
   int32_t order;                // 2 or 4
   int32_t laplacian_scale;
   int32_t n_tiles;
+  int32_t n_energy;             // number of (smooth, barrier) partials the tile kernel writes
   int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
   long long *dbg;               // optional [n_tiles][16] phase timestamps (developer tool), else nullptr
 };
@@ -34,6 +36,8 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 // One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
 cudaError_t prepare_energy_grad(int tile_tets);
 int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
+void set_use_v4(int v);           // developer switch: non-pipelined kernel for tile_tets 512
+int get_use_v4();
 void set_threads_512(int nt);
 void set_skip_combine(int v);
 

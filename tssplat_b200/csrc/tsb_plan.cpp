@@ -370,6 +370,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
     if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
     hd->ntet = ntet; hd->nvert = nv; hd->nrow = nrow; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
+    P.tile_ell.push_back(hd->ell_off); P.tile_ell.push_back(nell);
     for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
     P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
     // row index of (vertex, chunk 0); chunks of a vertex are NOT adjacent after sorting, so map each

@@ -51,6 +51,7 @@ struct HostPlan {
   // layout [group][k/2][lane][2] so one 32-bit load fetches two entries of a lane
   std::vector<uint16_t> ell;
   std::vector<int32_t> slot_ptr;    // [n+1] scratch slots of each vertex (combine kernel CSR)
+  std::vector<int32_t> tile_ell;    // [2*n_tiles] (ell_off, nell) per tile: lets the TMA producer size the copy
   std::vector<int32_t> tet_order;   // tile-order position -> original tet id
   std::vector<int32_t> tile_first;  // [n_tiles+1] position in tet_order of each tile's first tet
 };
