@@ -86,7 +86,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     if (opt->tile_tets != 0) po.tile_tets = opt->tile_tets;
     po.laplacian_scale = opt->laplacian_scale ? 1 : 0;
   }
-  if (const char *env = std::getenv("TSSPLAT_B200_V4")) tsb::set_use_v4(std::atoi(env));
+  if (const char *env = std::getenv("TSSPLAT_B200_PIPE")) tsb::set_use_v4(std::atoi(env) ? 0 : 1);
   if (const char *env = std::getenv("TSSPLAT_B200_TILE_TETS")) {
     if (!(opt && opt->tile_tets != 0)) po.tile_tets = std::atoi(env);
   }

@@ -90,8 +90,8 @@ struct Smem {
   static constexpr int NR = NV + 8 * TT / kRowCap;           // == rows_cap(TT, NV)
   static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;   // == ell_cap(TT, NV)
   static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
-  static constexpr int kVOff = 0;
-  static constexpr int kTOff = align_up(kVOff + kVBytes, 128);
+  static constexpr int kVStage = align_up(kVBytes, 128);     // two vertex-blob stages
+  static constexpr int kTOff = 2 * kVStage;
   static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
   static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
   static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
@@ -244,124 +244,141 @@ __device__ __forceinline__ void tet_body(const int lt, const uint4 *__restrict__
   }
 }
 
+// Tile kernel: persistent CTAs (MINB per SM), each looping over tiles b, b+G, b+2G, ...  The three
+// phases of a tile run in lock-step inside the CTA (they are all shared-memory heavy, so overlapping
+// them only makes them contend -- profiles/r01_summary.md), but every global access of tile j+1 is
+// in flight while tile j computes:
+//   * vertex blob j+1 (double buffered) is requested by TMA as soon as tile j-1 has been consumed,
+//   * tet blob j+1 the moment the tet math of tile j is done, the gather table of tile j right after
+//     the row gather of tile j-1,
+//   * the only dependent chain, vertex id -> x, is issued straight from global memory one phase ahead
+//     (ids at the top of tile j, x right after its tet math) and lands in registers.
 template <int TT, int NV, int NT, int MINB, bool WITH_GRAD>
 __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_constant__ KParams p) {
   using L = Smem<TT, NV>;
-  constexpr int NR = L::NR;
+  constexpr int NR = L::NR, TTP = L::kTTP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const TileHeader *hd = reinterpret_cast<const TileHeader *>(smem_raw + L::kVOff);
-  const float *Xx_s = reinterpret_cast<const float *>(smem_raw + L::kVOff + 64 + 4 * NV);
-  const float2 *xs2 = reinterpret_cast<const float2 *>(smem_raw + L::kVOff + 64 + 8 * NV);     // (Y, Z) rest
-  const int32_t *slot_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV);
-  const int32_t *grp_s = reinterpret_cast<const int32_t *>(smem_raw + L::kVOff + 64 + 16 * NV + 4 * NR);
   const uint4 *idx_s = reinterpret_cast<const uint4 *>(smem_raw + L::kTOff);
   const float *B_s = reinterpret_cast<const float *>(smem_raw + L::kTOff + 16 * TT);
   const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(smem_raw + L::kEllOff);
   float4 *xs4 = reinterpret_cast<float4 *>(smem_raw + L::kXs4Off);                               // x, y, z, X
   float *outb = reinterpret_cast<float *>(smem_raw + L::kOutOff);
-  __shared__ __align__(8) uint64_t s_bar[3];
+  __shared__ __align__(8) uint64_t bar_v[2], bar_t, bar_e;
   __shared__ float s_red[2 * (NT / 32)];
-  constexpr int TTP = L::kTTP;
 
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x;
-
-  if (p.dbg && tid == 0) { p.dbg[size_t(tile) * 16 + 14] = gtime_ns(); p.dbg[size_t(tile) * 16 + 13] = smid(); }
-  TSB_STAMP(0);
-  // Start the only dependent global chain (vertex id -> x) right away, straight from global memory
-  // and in parallel with the TMA staging below.  Entries past nvert are zero padding (-> x[0]).
+  const int G = int(gridDim.x);
+  const int n_my = (p.n_tiles - int(blockIdx.x) + G - 1) / G;
+  const uint32_t nt_b = uint32_t(p.fill);
   constexpr int kVPer = (NV + NT - 1) / NT;
-  int vid[kVPer];
-  {
-    const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(tile) * L::kVBytes + 64);
-#pragma unroll
-    for (int j = 0; j < kVPer; ++j) vid[j] = (tid + j * NT < NV) ? __ldg(vl_g + tid + j * NT) : 0;
-  }
 
-  // ---------------- stage the tile with TMA bulk copies ----------------------------------------
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1);
-    mbar_fence_init();
-    mbar_expect_tx(&s_bar[0], L::kVBytes);
-    bulk_g2s(smem_raw + L::kVOff, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &s_bar[0]);
-    const uint32_t nt_b = uint32_t(p.fill);
-    mbar_expect_tx(&s_bar[1], 52u * nt_b);
+  auto issue_v = [&](int j) {
+    const int tile = int(blockIdx.x) + j * G;
+    mbar_expect_tx(&bar_v[j & 1], L::kVBytes);
+    bulk_g2s(smem_raw + (j & 1) * L::kVStage, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[j & 1]);
+  };
+  auto issue_t = [&](int j) {
+    const int tile = int(blockIdx.x) + j * G;
+    mbar_expect_tx(&bar_t, 52u * nt_b);
     const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
-    bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &s_bar[1]);
-    bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &s_bar[1]);
-  }
+    bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &bar_t);
+    bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t);
+  };
+  auto issue_e = [&](int j) {
+    const int2 el = __ldg(p.tile_ell + int(blockIdx.x) + j * G);
+    mbar_expect_tx(&bar_e, 2u * uint32_t(el.y));
+    if (el.y > 0) bulk_g2s(smem_raw + L::kEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e);
+  };
+  auto load_vids = [&](int j, int (&vid)[kVPer]) {     // entries past nvert are zero padding (-> x[0])
+    const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(int(blockIdx.x) + j * G) * L::kVBytes + 64);
+#pragma unroll
+    for (int q = 0; q < kVPer; ++q) vid[q] = (tid + q * NT < NV) ? __ldg(vl_g + tid + q * NT) : 0;
+  };
+  auto load_x = [&](const int (&vid)[kVPer], float (&px)[kVPer][3]) {
+#pragma unroll
+    for (int q = 0; q < kVPer; ++q) {
+      const float *xp = p.x + 3 * size_t(vid[q]);
+      px[q][0] = __ldg(xp); px[q][1] = __ldg(xp + 1); px[q][2] = __ldg(xp + 2);
+    }
+  };
+
+  int vid[kVPer];
   float px[kVPer][3];
-#pragma unroll
-  for (int j = 0; j < kVPer; ++j) {
-    const float *xp = p.x + 3 * size_t(vid[j]);
-    px[j][0] = __ldg(xp); px[j][1] = __ldg(xp + 1); px[j][2] = __ldg(xp + 2);
+  if (n_my > 0) load_vids(0, vid);
+  if (tid == 0) {
+    mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1); mbar_init(&bar_t, 1); mbar_init(&bar_e, 1);
+    mbar_fence_init();
+    if (n_my > 0) { issue_v(0); issue_t(0); }
   }
-  __syncthreads();
-  TSB_STAMP(1);
-  mbar_wait(&s_bar[0], 0);
-  TSB_STAMP(2);
-  const int ntet = hd->ntet, nvert = hd->nvert;
-  const int nell = hd->nell;
-  if (WITH_GRAD && tid == 0 && nell > 0) {
-    mbar_expect_tx(&s_bar[2], 2u * uint32_t(nell));
-    bulk_g2s(smem_raw + L::kEllOff, p.ell + hd->ell_off, 2u * uint32_t(nell), &s_bar[2]);
-  }
-
-  // ---------------- phase 0: x (prefetched above) + rest X -> shared ---------------------------
   if (WITH_GRAD && tid < 3) outb[tid * TTP + TT] = 0.f;   // zero column for gather-table padding
-#pragma unroll
-  for (int j = 0; j < kVPer; ++j) {
-    const int i = tid + j * NT;
-    if (i < nvert) xs4[i] = make_float4(px[j][0], px[j][1], px[j][2], Xx_s[i]);
-  }
-  TSB_STAMP(3);
+  if (n_my > 0) load_x(vid, px);
   __syncthreads();
-  TSB_STAMP(4);
-  mbar_wait(&s_bar[1], 0);
-  TSB_STAMP(5);
 
-  // ---------------- phase 1: tets -----------------------------------------------------------------
   float es = 0.f, eb = 0.f;
   const float c1 = p.c1, c2 = p.c2;
   const int order = p.order;
   const bool lscale = p.laplacian_scale != 0;
-  for (int lt = tid; lt < ntet; lt += NT)
-    tet_body<TTP, WITH_GRAD>(lt, idx_s, B_s, xs4, xs2, outb, c1, c2, order, lscale, es, eb);
+  for (int j = 0; j < n_my; ++j) {
+    const unsigned char *vb = smem_raw + (j & 1) * L::kVStage;
+    const TileHeader *hd = reinterpret_cast<const TileHeader *>(vb);
+    const float *Xx_s = reinterpret_cast<const float *>(vb + 64 + 4 * NV);
+    const float2 *xs2 = reinterpret_cast<const float2 *>(vb + 64 + 8 * NV);                      // (Y, Z) rest
+    const int32_t *slot_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV);
+    const int32_t *grp_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV + 4 * NR);
+    if (j + 1 < n_my) load_vids(j + 1, vid);           // ids of the next tile: needed only after this tile's tet math
 
-  TSB_STAMP(6);
-  // per-tile energy partials (tree reduction; the cross-tile sum is done in fp64 below)
+    // ---------------- phase 0: x (already in registers) + rest X -> shared -------------------
+    mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
+    const int ntet = hd->ntet, nvert = hd->nvert, nrow = hd->nrow;
+#pragma unroll
+    for (int q = 0; q < kVPer; ++q) {
+      const int i = tid + q * NT;
+      if (i < nvert) xs4[i] = make_float4(px[q][0], px[q][1], px[q][2], Xx_s[i]);
+    }
+    __syncthreads();     // (A) xs4 complete; every thread has left the previous tile's row gather
+    if (tid == 0) {
+      if (j + 1 < n_my) issue_v(j + 1);               // its stage held tile j-1, now fully consumed
+      if (WITH_GRAD) issue_e(j);                       // gather-table buffer is free since (A)
+    }
+
+    // ---------------- phase 1: tets -----------------------------------------------------------------
+    mbar_wait(&bar_t, j & 1);
+    for (int lt = tid; lt < ntet; lt += NT)
+      tet_body<TTP, WITH_GRAD>(lt, idx_s, B_s, xs4, xs2, outb, c1, c2, order, lscale, es, eb);
+    __syncthreads();     // (B) output table complete; tet blob and xs4 are free
+    if (j + 1 < n_my) {
+      if (tid == 0) issue_t(j + 1);
+      load_x(vid, px);                                 // lands while the row gather below runs
+    } else {
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // last tile: let the combine kernel launch
+    }
+
+    // ---------------- phase 2: per-row gather --------------------------------------------------------
+    if (WITH_GRAD) {
+      mbar_wait(&bar_e, j & 1);
+      float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
+      for (int r = tid; r < nrow; r += NT) {
+        const int g = r >> 5, lane = r & 31;
+        const int beg = grp_s[g], end = grp_s[g + 1];
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
+        scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
+      }
+    }
+  }
+
+  // one (smooth, barrier) partial per CTA (tree reduction; the cross-CTA sum is done in fp64 by the combine kernel)
   {
     const float ws = warp_sum(es), wb = warp_sum(eb);
     if ((tid & 31) == 0) { s_red[tid >> 5] = ws; s_red[NT / 32 + (tid >> 5)] = wb; }
   }
   __syncthreads();
   if (tid < 32) {
-    float vs = (tid < NT / 32) ? s_red[tid] : 0.f, vb = (tid < NT / 32) ? s_red[NT / 32 + tid] : 0.f;
-    vs = warp_sum(vs); vb = warp_sum(vb);
-    if (tid == 0) { p.tile_energy[2 * tile] = vs; p.tile_energy[2 * tile + 1] = vb; }
+    float vs = (tid < NT / 32) ? s_red[tid] : 0.f, vb2 = (tid < NT / 32) ? s_red[NT / 32 + tid] : 0.f;
+    vs = warp_sum(vs); vb2 = warp_sum(vb2);
+    if (tid == 0) { p.tile_energy[2 * blockIdx.x] = vs; p.tile_energy[2 * blockIdx.x + 1] = vb2; }
   }
-
-  // let the combine kernel's CTAs start launching while this tile finishes
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  if (WITH_GRAD) {
-    // ---------------- phase 2: per-vertex gather ------------------------------------------------
-    TSB_STAMP(7);
-    if (nell > 0) mbar_wait(&s_bar[2], 0);
-    TSB_STAMP(8);
-    const int nrow = hd->nrow;
-    float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-    for (int r = tid; r < nrow; r += NT) {
-      const int g = r >> 5, lane = r & 31;
-      const int beg = grp_s[g], end = grp_s[g + 1];
-      const int len2 = (end - beg) >> 6;      // <= kRowCap / 2
-      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, len2, g0, g1, g2);
-      scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
-    }
-    TSB_STAMP(9);
-  }
-  if (p.dbg && tid == 0) p.dbg[size_t(tile) * 16 + 15] = gtime_ns();
+  if (n_my == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -384,13 +401,14 @@ struct PipeSmem {
   static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;
   static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
   static constexpr int kTTP = TT + 4;
-  static constexpr int kVOff = 0;
-  static constexpr int kTOff = align_up(kVOff + kVBytes, 128);
-  static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
-  static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
-  static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
-  static constexpr int kStageBytes = align_up(kOutOff + 96 * kTTP, 128);
-  static constexpr int kBytes = 2 * kStageBytes;
+  // vertex ring (3 stages): vertex blob | xs4 ; tet ring (2 stages): tet blob | gather table | output table
+  static constexpr int kVXs4Off = align_up(kVBytes, 128);
+  static constexpr int kVStageBytes = align_up(kVXs4Off + 16 * NV, 128);
+  static constexpr int kTEllOff = align_up(52 * TT, 128);
+  static constexpr int kTOutOff = align_up(kTEllOff + 2 * ELLCAP, 128);
+  static constexpr int kTStageBytes = align_up(kTOutOff + 96 * kTTP, 128);
+  static constexpr int kTRingOff = 3 * kVStageBytes;
+  static constexpr int kBytes = kTRingOff + 2 * kTStageBytes;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -413,22 +431,50 @@ __global__ void __launch_bounds__(kPipeThreads, 1) energy_grad_pipe_kernel(const
   using L = PipeSmem<TT, NV>;
   constexpr int NR = L::NR, TTP = L::kTTP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_v[2], bar_t[2], bar_e[2], bar_x[2], bar_out[2], bar_free[2];
+  // tile k uses vertex stage k % 3 (use count k / 3) and tet stage k & 1 (use count k >> 1)
+  __shared__ __align__(8) uint64_t bar_v[3], bar_x[3], bar_t[2], bar_e[2], bar_out[2], bar_free[2];
   __shared__ float s_red[2 * kPipeComputeWarps];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_my = (p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles b, b+G, b+2G, ...
+  const uint32_t nt_b = uint32_t(p.fill);
 
-  if (tid == 0) {
+  auto issue_v = [&](int k) {       // vertex blob of tile k -> vertex stage k % 3
+    const int vs = k % 3;
+    const int tile = int(blockIdx.x) + k * int(gridDim.x);
+    mbar_expect_tx(&bar_v[vs], L::kVBytes);
+    bulk_g2s(smem_raw + vs * L::kVStageBytes, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[vs]);
+  };
+  auto issue_t = [&](int k) {       // tet blob + gather table of tile k -> tet stage k & 1
+    const int s = k & 1;
+    const int tile = int(blockIdx.x) + k * int(gridDim.x);
+    unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
+    mbar_expect_tx(&bar_t[s], 52u * nt_b);
+    const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
+    bulk_g2s(st, tb, 16u * nt_b, &bar_t[s]);
+    bulk_g2s(st + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t[s]);
+    if (WITH_GRAD) {
+      const int2 el = __ldg(p.tile_ell + tile);
+      mbar_expect_tx(&bar_e[s], 2u * uint32_t(el.y));
+      if (el.y > 0) bulk_g2s(st + L::kTEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e[s]);
+    }
+  };
+
+  if (tid == kPipeComputeWarps * 32) {   // the producer thread initialises the barriers and fires the first copies
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { mbar_init(&bar_v[s], 1); mbar_init(&bar_x[s], kPipeAuxWarps); }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_v[s], 1); mbar_init(&bar_t[s], 1); mbar_init(&bar_e[s], 1);
-      mbar_init(&bar_x[s], kPipeAuxWarps); mbar_init(&bar_out[s], kPipeComputeWarps); mbar_init(&bar_free[s], kPipeAuxWarps);
+      mbar_init(&bar_t[s], 1); mbar_init(&bar_e[s], 1);
+      mbar_init(&bar_out[s], kPipeComputeWarps); mbar_init(&bar_free[s], kPipeAuxWarps);
     }
     mbar_fence_init();
+    for (int k = 0; k < 3 && k < n_my; ++k) issue_v(k);
+    for (int k = 0; k < 2 && k < n_my; ++k) issue_t(k);
   }
-  if (WITH_GRAD && tid < 6) {   // zero columns of both stages' output tables (gather-table padding target)
-    float *ob = reinterpret_cast<float *>(smem_raw + (tid / 3) * L::kStageBytes + L::kOutOff);
+  if (p.dbg && tid == 0) p.dbg[size_t(blockIdx.x) * 64 + 63] = clock64();
+  if (WITH_GRAD && tid < 6) {   // zero columns of both output tables (gather-table padding target)
+    float *ob = reinterpret_cast<float *>(smem_raw + L::kTRingOff + (tid / 3) * L::kTStageBytes + L::kTOutOff);
     ob[(tid % 3) * TTP + TT] = 0.f;
   }
   __syncthreads();
@@ -440,90 +486,80 @@ __global__ void __launch_bounds__(kPipeThreads, 1) energy_grad_pipe_kernel(const
     const int order = p.order;
     const bool lscale = p.laplacian_scale != 0;
     for (int k = 0; k < n_my; ++k) {
-      const int s = k & 1;
-      const uint32_t par = (k >> 1) & 1;
-      unsigned char *st = smem_raw + s * L::kStageBytes;
-      mbar_wait_guard(&bar_x[s], par);      // x of this tile staged (implies the vertex blob landed)
-      mbar_wait_guard(&bar_t[s], par);      // tet blob landed
-      const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
-      const int ntet = hd->ntet;
+      const int s = k & 1, vs = k % 3;
+      unsigned char *sv = smem_raw + vs * L::kVStageBytes;
+      unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
+      mbar_wait_guard(&bar_x[vs], (k / 3) & 1);      // x of this tile staged (implies the vertex blob landed)
+      mbar_wait_guard(&bar_t[s], (k >> 1) & 1);      // tet blob landed
+      if (p.dbg && tid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 2] = clock64();
+      const int ntet = reinterpret_cast<const TileHeader *>(sv)->ntet;
       if (tid < ntet)
-        tet_body<TTP, WITH_GRAD>(tid, reinterpret_cast<const uint4 *>(st + L::kTOff),
-                                 reinterpret_cast<const float *>(st + L::kTOff + 16 * TT),
-                                 reinterpret_cast<const float4 *>(st + L::kXs4Off),
-                                 reinterpret_cast<const float2 *>(st + L::kVOff + 64 + 8 * NV),
-                                 reinterpret_cast<float *>(st + L::kOutOff), c1, c2, order, lscale, es, eb);
+        tet_body<TTP, WITH_GRAD>(tid, reinterpret_cast<const uint4 *>(st), reinterpret_cast<const float *>(st + 16 * TT),
+                                 reinterpret_cast<const float4 *>(sv + L::kVXs4Off),
+                                 reinterpret_cast<const float2 *>(sv + 64 + 8 * NV),
+                                 reinterpret_cast<float *>(st + L::kTOutOff), c1, c2, order, lscale, es, eb);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_out[s]);
+      if (p.dbg && tid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 3] = clock64();
     }
     // one (smooth, barrier) partial per CTA
     const float ws = warp_sum(es), wb = warp_sum(eb);
     if (lane == 0) { s_red[warp] = ws; s_red[kPipeComputeWarps + warp] = wb; }
     asm volatile("bar.sync 1, %0;" ::"n"(kPipeComputeWarps * 32) : "memory");
     if (warp == 0) {
-      float vs = (lane < kPipeComputeWarps) ? s_red[lane] : 0.f, vb = (lane < kPipeComputeWarps) ? s_red[kPipeComputeWarps + lane] : 0.f;
-      vs = warp_sum(vs); vb = warp_sum(vb);
-      if (lane == 0) { p.tile_energy[2 * blockIdx.x] = vs; p.tile_energy[2 * blockIdx.x + 1] = vb; }
+      float vs_ = (lane < kPipeComputeWarps) ? s_red[lane] : 0.f, vb = (lane < kPipeComputeWarps) ? s_red[kPipeComputeWarps + lane] : 0.f;
+      vs_ = warp_sum(vs_); vb = warp_sum(vb);
+      if (lane == 0) { p.tile_energy[2 * blockIdx.x] = vs_; p.tile_energy[2 * blockIdx.x + 1] = vb; }
     }
   } else if (warp == kPipeComputeWarps) {
     // ======================= producer: TMA staging ================================================
+    // When tile k-2 has been fully consumed its tet stage takes tile k and its vertex stage
+    // ((k-2) % 3 == (k+1) % 3) takes tile k+1.
     if (lane == 0) {
-      const uint32_t nt_b = uint32_t(p.fill);
-      for (int k = 0; k < n_my; ++k) {
-        const int s = k & 1;
-        const int tile = int(blockIdx.x) + k * int(gridDim.x);
-        unsigned char *st = smem_raw + s * L::kStageBytes;
-        const int2 el = __ldg(p.tile_ell + tile);
-        if (k >= 2) mbar_wait_guard(&bar_free[s], ((k >> 1) - 1) & 1);   // previous tile in this stage fully consumed
-        mbar_expect_tx(&bar_v[s], L::kVBytes);
-        bulk_g2s(st + L::kVOff, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[s]);
-        mbar_expect_tx(&bar_t[s], 52u * nt_b);
-        const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
-        bulk_g2s(st + L::kTOff, tb, 16u * nt_b, &bar_t[s]);
-        bulk_g2s(st + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t[s]);
-        if (WITH_GRAD) {
-          mbar_expect_tx(&bar_e[s], 2u * uint32_t(el.y));
-          if (el.y > 0) bulk_g2s(st + L::kEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e[s]);
-        }
+      for (int k = 2; k < n_my; ++k) {
+        mbar_wait_guard(&bar_free[k & 1], ((k >> 1) - 1) & 1);
+        if (p.dbg && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 6] = clock64();
+        issue_t(k);
+        if (k + 1 < n_my) issue_v(k + 1);
       }
     }
   } else {
-    // ======================= aux warps: x gather (tile k+1) and row gather (tile k) ===============
+    // ======================= aux warps: x gather (two tiles ahead) and row gather ==================
     constexpr int NA = kPipeAuxWarps * 32;
     const int atid = tid - (kPipeComputeWarps + 1) * 32;
     auto stage_x = [&](int k) {
-      const int s = k & 1;
-      const uint32_t par = (k >> 1) & 1;
-      unsigned char *st = smem_raw + s * L::kStageBytes;
-      mbar_wait_guard(&bar_v[s], par);
-      const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
-      const int32_t *vlist_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64);
-      const float *Xx_s = reinterpret_cast<const float *>(st + L::kVOff + 64 + 4 * NV);
-      float4 *xs4 = reinterpret_cast<float4 *>(st + L::kXs4Off);
-      const int nvert = hd->nvert;
+      const int vs = k % 3;
+      unsigned char *sv = smem_raw + vs * L::kVStageBytes;
+      mbar_wait_guard(&bar_v[vs], (k / 3) & 1);
+      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 0] = clock64();
+      const int32_t *vlist_s = reinterpret_cast<const int32_t *>(sv + 64);
+      const float *Xx_s = reinterpret_cast<const float *>(sv + 64 + 4 * NV);
+      float4 *xs4 = reinterpret_cast<float4 *>(sv + L::kVXs4Off);
+      const int nvert = reinterpret_cast<const TileHeader *>(sv)->nvert;
       for (int i = atid; i < nvert; i += NA) {
         const float *xp = p.x + 3 * size_t(vlist_s[i]);
         xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_x[s]);
+      if (lane == 0) mbar_arrive(&bar_x[vs]);
+      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 1] = clock64();
     };
     if (n_my > 0) stage_x(0);
+    if (n_my > 1) stage_x(1);
     for (int k = 0; k < n_my; ++k) {
-      if (k + 1 < n_my) stage_x(k + 1);
       const int s = k & 1;
-      const uint32_t par = (k >> 1) & 1;
-      unsigned char *st = smem_raw + s * L::kStageBytes;
-      mbar_wait_guard(&bar_out[s], par);           // compute warps finished this tile's table
+      unsigned char *sv = smem_raw + (k % 3) * L::kVStageBytes;
+      unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
+      mbar_wait_guard(&bar_out[s], (k >> 1) & 1);           // compute warps finished this tile's table
+      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 4] = clock64();
       if (WITH_GRAD) {
-        mbar_wait_guard(&bar_e[s], par);
-        const TileHeader *hd = reinterpret_cast<const TileHeader *>(st + L::kVOff);
-        const int32_t *slot_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64 + 16 * NV);
-        const int32_t *grp_s = reinterpret_cast<const int32_t *>(st + L::kVOff + 64 + 16 * NV + 4 * NR);
-        const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(st + L::kEllOff);
-        const float *outb = reinterpret_cast<const float *>(st + L::kOutOff);
+        mbar_wait_guard(&bar_e[s], (k >> 1) & 1);
+        const int32_t *slot_s = reinterpret_cast<const int32_t *>(sv + 64 + 16 * NV);
+        const int32_t *grp_s = reinterpret_cast<const int32_t *>(sv + 64 + 16 * NV + 4 * NR);
+        const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(st + L::kTEllOff);
+        const float *outb = reinterpret_cast<const float *>(st + L::kTOutOff);
         float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-        const int nrow = hd->nrow;
+        const int nrow = reinterpret_cast<const TileHeader *>(sv)->nrow;
         for (int r = atid; r < nrow; r += NA) {
           const int g = r >> 5, ln = r & 31;
           const int beg = grp_s[g], end = grp_s[g + 1];
@@ -533,7 +569,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) energy_grad_pipe_kernel(const
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_free[s]);    // vertex blob, tet blob, table, gather table: all reusable
+      if (lane == 0) mbar_arrive(&bar_free[s]);    // tile k fully consumed: its tet stage and vertex stage are reusable
+      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 5] = clock64();
+      if (k + 2 < n_my) stage_x(k + 2);            // its vertex blob was requested one tile ago
     }
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -661,7 +699,7 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
 
 // Compiled variants: tile capacity TT -> staged-vertex capacity NV (then threads, min CTAs/SM)
 #define TSB_V256 256, 256
-#define TSB_V512 512, 384
+#define TSB_V512 512, 256
 #define TSB_V1024 1024, 640
 
 cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
@@ -683,10 +721,12 @@ cudaError_t launch_pipe(const KParams &p0, int n_vertices, const int32_t *slot_p
 template <int TT, int NV, int NT, int MINB>
 cudaError_t launch_variant(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   KParams p = p0;
-  p.n_energy = p.n_tiles;
+  const int slots = MINB * g_num_sms;
+  const int grid = p.n_tiles < slots ? p.n_tiles : slots;
+  p.n_energy = grid;
   const int smem = Smem<TT, NV>::kBytes;
-  if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<p.n_tiles, NT, smem, stream>>>(p);
-  else energy_grad_kernel<TT, NV, NT, MINB, false><<<p.n_tiles, NT, smem, stream>>>(p);
+  if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<grid, NT, smem, stream>>>(p);
+  else energy_grad_kernel<TT, NV, NT, MINB, false><<<grid, NT, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || g_skip_combine) return e;
   return launch_combine(p, n_vertices, slot_ptr, stream);
@@ -724,14 +764,14 @@ inline int grid_for(int64_t count, int block) {
 
 }  // namespace
 
-static int g_use_v4 = 0;
+static int g_use_v4 = 1;   // 1 = lock-step persistent kernel (default); 0 = warp-specialised pipeline (experimental)
 void set_use_v4(int v) { g_use_v4 = v; }
 int get_use_v4() { return g_use_v4; }
 
 int nvmax_for(int tile_tets) {
   switch (tile_tets) {
     case 256: return 256;
-    case 512: return g_use_v4 ? 384 : 256;   // pipelined kernel stages 2 tiles -> smaller vertex capacity
+    case 512: return 256;
     case 1024: return 640;
   }
   return 0;
@@ -740,11 +780,13 @@ int nvmax_for(int tile_tets) {
 static int g_threads_512 = 256;
 
 cudaError_t prepare_energy_grad(int tile_tets) {
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+  }
   switch (tile_tets) {
     case 256: return prepare_variant<TSB_V256, 256, 3>();
     case 512: {
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
       cudaError_t e = prepare_variant<TSB_V512, 256, 2>();
       if (e != cudaSuccess) return e;
       e = prepare_variant<TSB_V512, 512, 1>();
