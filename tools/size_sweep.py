@@ -1,4 +1,4 @@
-"""Kernel time vs pack size for the pipelined (v5) and one-tile-per-CTA (v4) tile kernels (developer tool)."""
+"""Step / tile-kernel time vs pack size for the compiled tile variants (developer tool)."""
 import ctypes, os, sys
 import numpy as np
 import torch
@@ -31,8 +31,7 @@ for S in [int(a) for a in sys.argv[1:]] or [16, 64, 256, 1024]:
     pack = make_pack(S, 4096, seed=0, unique=8)
     x = torch.from_numpy(perturb(pack, sigma_rel=0.02, seed=0)).cuda()
     balg = pack.algorithmic_bytes()
-    for v4, tt in ((0, 512), (1, 512), (1, 256), (1, 1024)):
-        lib.tsb_debug_set_use_v4(ctypes.c_int(v4))
+    for v4, tt in ((1, 512), (1, 256), (1, 1024)):
         sp = ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1), tile_tets=tt)
         reps = max(4, min(200, int(4000 / S)))
         res = []
@@ -40,7 +39,6 @@ for S in [int(a) for a in sys.argv[1:]] or [16, 64, 256, 1024]:
             lib.tsb_debug_set_skip_combine(ctypes.c_int(skip))
             res.append(bench(sp, x, S, reps))
         lib.tsb_debug_set_skip_combine(ctypes.c_int(0))
-        print(f"S={S:5d} {'v4' if v4 else 'v5'} TT={tt:4d} tiles={sp.info['n_tiles']:6d} fill={sp.info['fill']:4d}: step {res[0]:8.2f} us "
+        print(f"S={S:5d} TT={tt:4d} tiles={sp.info['n_tiles']:6d} fill={sp.info['fill']:4d}: step {res[0]:8.2f} us "
               f"(tile kernel only {res[1]:8.2f} us)  B_alg {balg/1e6:7.1f} MB -> {balg/res[0]/1e3:6.0f} GB/s = {balg/res[0]/1e3/6573.2:.3f} of HBM peak", flush=True)
         del sp
-    lib.tsb_debug_set_use_v4(ctypes.c_int(0))

@@ -86,7 +86,6 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     if (opt->tile_tets != 0) po.tile_tets = opt->tile_tets;
     po.laplacian_scale = opt->laplacian_scale ? 1 : 0;
   }
-  if (const char *env = std::getenv("TSSPLAT_B200_PIPE")) tsb::set_use_v4(std::atoi(env) ? 0 : 1);
   if (const char *env = std::getenv("TSSPLAT_B200_TILE_TETS")) {
     if (!(opt && opt->tile_tets != 0)) po.tile_tets = std::atoi(env);
   }
@@ -262,13 +261,9 @@ int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {  /* out8: 10 in
 
 void tsb_debug_plan_free(tsb_debug_plan_s *d) { delete d; }
 
-/* Developer tool: device buffer of [n_tiles][16] int64 phase stamps written by the next launches
- * (NULL switches it off).  Not part of the stable ABI. */
-void tsb_debug_set_timing(tsb_handle_t h, long long *dbg_dev) { if (h) h->kp.dbg = dbg_dev; }
-
 /* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
 void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
 void tsb_debug_set_skip_combine(int v) { tsb::set_skip_combine(v); }
-void tsb_debug_set_use_v4(int v) { tsb::set_use_v4(v); }
+
 
 }  // extern "C"

@@ -18,20 +18,22 @@
 // passes, no grid sync.  The barrier term is the reference's: max(-det F,0)^p, p in {2,4}
 // (cu:48-66), gradient -p(-J)^(p-1) cof(F) (cu:68-102).
 //
-// Execution.  One CTA per tile (<= TT tets, <= NV staged vertices).  At kernel start one thread
-// issues TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the tile's vertex blob, tet blob
-// and gather table from global to shared memory; every later phase reads only shared memory.
-//   phase 0  gather x through the staged vertex list (the only indirection left in global memory)
+// Execution.  Persistent CTAs (2 per SM, 256 threads) loop over tiles of <= TT tets / <= NV staged
+// vertices.  One thread issues TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of each tile's
+// vertex blob, tet blob and gather table from global to shared memory one tile ahead; the only
+// dependent global chain (vertex id -> x) is issued one phase ahead and lands in registers.
+//   phase 0  x (registers) + rest X (staged) -> float4 array in shared memory
 //   phase 1  one tet per thread, branch-free: 13 smem gathers, energy terms, 8 output 3-vectors
-//            written to a [24][TT] smem table (conflict-free stores)
-//   phase 2  one staged vertex per thread: sum its table entries through a 32-wide sliced-ELL
-//            list (deterministic order) and store the tile's partial gradient of that vertex to
-//            its own float4 scratch slot
+//            written to a [24][TT+4] smem table (conflict-free stores)
+//   phase 2  one gather row per thread (<= 16 entries, bank-aware order, padding -> zero column):
+//            sum the table entries and store the partial gradient to the row's float4 scratch slot
 // A second, tiny kernel chained with programmatic dependent launch (griddepcontrol) sums each
-// vertex's slots in fixed order into grad (scaled by gradH) and folds the per-tile energies in
-// fp64.  No atomics, no fences, no grid sync: bitwise deterministic.  (Round-1 profile
-// profiles/r01_v2_single_launch.md: doing that combine inside the first kernel with a
-// last-arriver scheme cost 47% of warp time in fences, atomics and CTA barriers.)
+// vertex's slots in fixed order into grad (scaled by gradH) and folds the per-CTA energies in
+// fp64.  No atomics, no fences, no grid sync: bitwise deterministic.
+// History (profiles/r01_summary.md): a single-launch last-arriver combine cost 47% of warp time in
+// fences/atomics/barriers; a warp-specialised pipeline that overlapped the phases lost to shared-
+// memory contention (row gather 1.5k -> 4.3k cycles when it overlaps the tet math); overlapping
+// only the global-memory latency (this design) won.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -81,9 +83,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 int g_skip_combine = 0;   // developer switch (timing experiments only)
 
-__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
-#define TSB_STAMP(slot) do { if (p.dbg && tid == 0) p.dbg[size_t(tile) * 16 + (slot)] = clock64(); } while (0)
+
 
 template <int TT, int NV>
 struct Smem {
@@ -381,202 +381,6 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   if (n_my == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Pipelined tile kernel: one persistent CTA per SM, 24 warps with fixed roles, a two-stage shared
-// memory ring per CTA, everything synchronised with mbarriers (no CTA-wide barrier in the loop).
-//   warps 0..15  compute : phase 1 (tet math) of tile k, one tet per thread, back to back
-//   warp  16     producer: TMA bulk copies of tile k+1 / k+2 blobs as soon as a stage is free
-//   warps 17..23 aux     : x gather of tile k+1 (global -> smem) and row gather of tile k (smem ->
-//                          scratch) while the compute warps are busy with the tet math
-// Why: with one tile per CTA the three phases run in lock-step on all resident CTAs, so the
-// latency-bound phases (0 and 2) cannot hide behind the issue-bound phase 1
-// (profiles/r01_summary.md: 9.9k cycles per tile of which phase 1 is 4.6k).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kPipeComputeWarps = 16, kPipeAuxWarps = 7;
-constexpr int kPipeThreads = (kPipeComputeWarps + 1 + kPipeAuxWarps) * 32;   // 768
-
-template <int TT, int NV>
-struct PipeSmem {
-  static constexpr int NR = NV + 8 * TT / kRowCap;
-  static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;
-  static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
-  static constexpr int kTTP = TT + 4;
-  // vertex ring (3 stages): vertex blob | xs4 ; tet ring (2 stages): tet blob | gather table | output table
-  static constexpr int kVXs4Off = align_up(kVBytes, 128);
-  static constexpr int kVStageBytes = align_up(kVXs4Off + 16 * NV, 128);
-  static constexpr int kTEllOff = align_up(52 * TT, 128);
-  static constexpr int kTOutOff = align_up(kTEllOff + 2 * ELLCAP, 128);
-  static constexpr int kTStageBytes = align_up(kTOutOff + 96 * kTTP, 128);
-  static constexpr int kTRingOff = 3 * kVStageBytes;
-  static constexpr int kBytes = kTRingOff + 2 * kTStageBytes;
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a protocol bug traps (error to the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait_guard(uint64_t *bar, uint32_t parity) {
-  uint32_t ok, spins = 0;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    if (!ok && ++spins > (1u << 22)) __trap();
-  } while (!ok);
-}
-
-template <int TT, int NV, bool WITH_GRAD>
-__global__ void __launch_bounds__(kPipeThreads, 1) energy_grad_pipe_kernel(const __grid_constant__ KParams p) {
-  using L = PipeSmem<TT, NV>;
-  constexpr int NR = L::NR, TTP = L::kTTP;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // tile k uses vertex stage k % 3 (use count k / 3) and tet stage k & 1 (use count k >> 1)
-  __shared__ __align__(8) uint64_t bar_v[3], bar_x[3], bar_t[2], bar_e[2], bar_out[2], bar_free[2];
-  __shared__ float s_red[2 * kPipeComputeWarps];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_my = (p.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // tiles b, b+G, b+2G, ...
-  const uint32_t nt_b = uint32_t(p.fill);
-
-  auto issue_v = [&](int k) {       // vertex blob of tile k -> vertex stage k % 3
-    const int vs = k % 3;
-    const int tile = int(blockIdx.x) + k * int(gridDim.x);
-    mbar_expect_tx(&bar_v[vs], L::kVBytes);
-    bulk_g2s(smem_raw + vs * L::kVStageBytes, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[vs]);
-  };
-  auto issue_t = [&](int k) {       // tet blob + gather table of tile k -> tet stage k & 1
-    const int s = k & 1;
-    const int tile = int(blockIdx.x) + k * int(gridDim.x);
-    unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
-    mbar_expect_tx(&bar_t[s], 52u * nt_b);
-    const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
-    bulk_g2s(st, tb, 16u * nt_b, &bar_t[s]);
-    bulk_g2s(st + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t[s]);
-    if (WITH_GRAD) {
-      const int2 el = __ldg(p.tile_ell + tile);
-      mbar_expect_tx(&bar_e[s], 2u * uint32_t(el.y));
-      if (el.y > 0) bulk_g2s(st + L::kTEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e[s]);
-    }
-  };
-
-  if (tid == kPipeComputeWarps * 32) {   // the producer thread initialises the barriers and fires the first copies
-#pragma unroll
-    for (int s = 0; s < 3; ++s) { mbar_init(&bar_v[s], 1); mbar_init(&bar_x[s], kPipeAuxWarps); }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_t[s], 1); mbar_init(&bar_e[s], 1);
-      mbar_init(&bar_out[s], kPipeComputeWarps); mbar_init(&bar_free[s], kPipeAuxWarps);
-    }
-    mbar_fence_init();
-    for (int k = 0; k < 3 && k < n_my; ++k) issue_v(k);
-    for (int k = 0; k < 2 && k < n_my; ++k) issue_t(k);
-  }
-  if (p.dbg && tid == 0) p.dbg[size_t(blockIdx.x) * 64 + 63] = clock64();
-  if (WITH_GRAD && tid < 6) {   // zero columns of both output tables (gather-table padding target)
-    float *ob = reinterpret_cast<float *>(smem_raw + L::kTRingOff + (tid / 3) * L::kTStageBytes + L::kTOutOff);
-    ob[(tid % 3) * TTP + TT] = 0.f;
-  }
-  __syncthreads();
-
-  if (warp < kPipeComputeWarps) {
-    // ======================= compute warps: phase 1 ===============================================
-    float es = 0.f, eb = 0.f;
-    const float c1 = p.c1, c2 = p.c2;
-    const int order = p.order;
-    const bool lscale = p.laplacian_scale != 0;
-    for (int k = 0; k < n_my; ++k) {
-      const int s = k & 1, vs = k % 3;
-      unsigned char *sv = smem_raw + vs * L::kVStageBytes;
-      unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
-      mbar_wait_guard(&bar_x[vs], (k / 3) & 1);      // x of this tile staged (implies the vertex blob landed)
-      mbar_wait_guard(&bar_t[s], (k >> 1) & 1);      // tet blob landed
-      if (p.dbg && tid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 2] = clock64();
-      const int ntet = reinterpret_cast<const TileHeader *>(sv)->ntet;
-      if (tid < ntet)
-        tet_body<TTP, WITH_GRAD>(tid, reinterpret_cast<const uint4 *>(st), reinterpret_cast<const float *>(st + 16 * TT),
-                                 reinterpret_cast<const float4 *>(sv + L::kVXs4Off),
-                                 reinterpret_cast<const float2 *>(sv + 64 + 8 * NV),
-                                 reinterpret_cast<float *>(st + L::kTOutOff), c1, c2, order, lscale, es, eb);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_out[s]);
-      if (p.dbg && tid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 3] = clock64();
-    }
-    // one (smooth, barrier) partial per CTA
-    const float ws = warp_sum(es), wb = warp_sum(eb);
-    if (lane == 0) { s_red[warp] = ws; s_red[kPipeComputeWarps + warp] = wb; }
-    asm volatile("bar.sync 1, %0;" ::"n"(kPipeComputeWarps * 32) : "memory");
-    if (warp == 0) {
-      float vs_ = (lane < kPipeComputeWarps) ? s_red[lane] : 0.f, vb = (lane < kPipeComputeWarps) ? s_red[kPipeComputeWarps + lane] : 0.f;
-      vs_ = warp_sum(vs_); vb = warp_sum(vb);
-      if (lane == 0) { p.tile_energy[2 * blockIdx.x] = vs_; p.tile_energy[2 * blockIdx.x + 1] = vb; }
-    }
-  } else if (warp == kPipeComputeWarps) {
-    // ======================= producer: TMA staging ================================================
-    // When tile k-2 has been fully consumed its tet stage takes tile k and its vertex stage
-    // ((k-2) % 3 == (k+1) % 3) takes tile k+1.
-    if (lane == 0) {
-      for (int k = 2; k < n_my; ++k) {
-        mbar_wait_guard(&bar_free[k & 1], ((k >> 1) - 1) & 1);
-        if (p.dbg && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 6] = clock64();
-        issue_t(k);
-        if (k + 1 < n_my) issue_v(k + 1);
-      }
-    }
-  } else {
-    // ======================= aux warps: x gather (two tiles ahead) and row gather ==================
-    constexpr int NA = kPipeAuxWarps * 32;
-    const int atid = tid - (kPipeComputeWarps + 1) * 32;
-    auto stage_x = [&](int k) {
-      const int vs = k % 3;
-      unsigned char *sv = smem_raw + vs * L::kVStageBytes;
-      mbar_wait_guard(&bar_v[vs], (k / 3) & 1);
-      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 0] = clock64();
-      const int32_t *vlist_s = reinterpret_cast<const int32_t *>(sv + 64);
-      const float *Xx_s = reinterpret_cast<const float *>(sv + 64 + 4 * NV);
-      float4 *xs4 = reinterpret_cast<float4 *>(sv + L::kVXs4Off);
-      const int nvert = reinterpret_cast<const TileHeader *>(sv)->nvert;
-      for (int i = atid; i < nvert; i += NA) {
-        const float *xp = p.x + 3 * size_t(vlist_s[i]);
-        xs4[i] = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), Xx_s[i]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_x[vs]);
-      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 1] = clock64();
-    };
-    if (n_my > 0) stage_x(0);
-    if (n_my > 1) stage_x(1);
-    for (int k = 0; k < n_my; ++k) {
-      const int s = k & 1;
-      unsigned char *sv = smem_raw + (k % 3) * L::kVStageBytes;
-      unsigned char *st = smem_raw + L::kTRingOff + s * L::kTStageBytes;
-      mbar_wait_guard(&bar_out[s], (k >> 1) & 1);           // compute warps finished this tile's table
-      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 4] = clock64();
-      if (WITH_GRAD) {
-        mbar_wait_guard(&bar_e[s], (k >> 1) & 1);
-        const int32_t *slot_s = reinterpret_cast<const int32_t *>(sv + 64 + 16 * NV);
-        const int32_t *grp_s = reinterpret_cast<const int32_t *>(sv + 64 + 16 * NV + 4 * NR);
-        const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(st + L::kTEllOff);
-        const float *outb = reinterpret_cast<const float *>(st + L::kTOutOff);
-        float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-        const int nrow = reinterpret_cast<const TileHeader *>(sv)->nrow;
-        for (int r = atid; r < nrow; r += NA) {
-          const int g = r >> 5, ln = r & 31;
-          const int beg = grp_s[g], end = grp_s[g + 1];
-          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-          gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + ln, (end - beg) >> 6, g0, g1, g2);
-          scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_free[s]);    // tile k fully consumed: its tet stage and vertex stage are reusable
-      if (p.dbg && atid == 0 && k < 8) p.dbg[size_t(blockIdx.x) * 64 + k * 8 + 5] = clock64();
-      if (k + 2 < n_my) stage_x(k + 2);            // its vertex blob was requested one tile ago
-    }
-  }
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-
 // Combine kernel: grad[v] = gradH * sum of v's scratch slots (fixed order); block 0 also folds the
 // per-tile energies in fp64.  Launched with programmatic stream serialization right behind the
 // tile kernel; griddepcontrol.wait blocks until that grid has completed and flushed.
@@ -705,19 +509,6 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
 cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
 int g_num_sms = 148;
 
-template <int TT, int NV>
-cudaError_t launch_pipe(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
-  KParams p = p0;
-  const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  p.n_energy = grid;
-  const int smem = PipeSmem<TT, NV>::kBytes;
-  if (p.grad) energy_grad_pipe_kernel<TT, NV, true><<<grid, kPipeThreads, smem, stream>>>(p);
-  else energy_grad_pipe_kernel<TT, NV, false><<<grid, kPipeThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess || g_skip_combine) return e;
-  return launch_combine(p, n_vertices, slot_ptr, stream);
-}
-
 template <int TT, int NV, int NT, int MINB>
 cudaError_t launch_variant(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   KParams p = p0;
@@ -764,10 +555,6 @@ inline int grid_for(int64_t count, int block) {
 
 }  // namespace
 
-static int g_use_v4 = 1;   // 1 = lock-step persistent kernel (default); 0 = warp-specialised pipeline (experimental)
-void set_use_v4(int v) { g_use_v4 = v; }
-int get_use_v4() { return g_use_v4; }
-
 int nvmax_for(int tile_tets) {
   switch (tile_tets) {
     case 256: return 256;
@@ -789,12 +576,7 @@ cudaError_t prepare_energy_grad(int tile_tets) {
     case 512: {
       cudaError_t e = prepare_variant<TSB_V512, 256, 2>();
       if (e != cudaSuccess) return e;
-      e = prepare_variant<TSB_V512, 512, 1>();
-      if (e != cudaSuccess) return e;
-      const int smem = PipeSmem<512, 256>::kBytes;
-      e = cudaFuncSetAttribute(energy_grad_pipe_kernel<512, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      return cudaFuncSetAttribute(energy_grad_pipe_kernel<512, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      return prepare_variant<TSB_V512, 512, 1>();
     }
     case 1024: return prepare_variant<TSB_V1024, 512, 1>();
   }
@@ -805,7 +587,6 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
   switch (tile_tets) {
     case 256: return launch_variant<TSB_V256, 256, 3>(p, n_vertices, slot_ptr, stream);
     case 512:
-      if (!g_use_v4) return launch_pipe<512, 256>(p, n_vertices, slot_ptr, stream);
       return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, n_vertices, slot_ptr, stream) : launch_variant<TSB_V512, 256, 2>(p, n_vertices, slot_ptr, stream);
     case 1024: return launch_variant<TSB_V1024, 512, 1>(p, n_vertices, slot_ptr, stream);
   }

@@ -28,7 +28,6 @@ struct KParams {
   int32_t n_tiles;
   int32_t n_energy;             // number of (smooth, barrier) partials the tile kernel writes
   int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
-  long long *dbg;               // optional [n_tiles][16] phase timestamps (developer tool), else nullptr
 };
 
 // Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
@@ -36,8 +35,7 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 // One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
 cudaError_t prepare_energy_grad(int tile_tets);
 int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
-void set_use_v4(int v);           // developer switch: non-pipelined kernel for tile_tets 512
-int get_use_v4();
+
 void set_threads_512(int nt);
 void set_skip_combine(int v);
 
