@@ -96,12 +96,13 @@ int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH
 int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, void *stream);
 
 /* "Next" row (f)1: AdamUniform.step (utils/optimizer.py:37-89) as two launches and no sync.
- * p, g1, g2: device float32 [count]; step is the 1-based step number AFTER increment.
+ * p, g1, g2: device float32 [count]; step is the 1-based step number AFTER increment.  lr and the
+ * betas are doubles (Python floats) so that 1-beta and the bias corrections round as in the reference.
  * grad_limit <= 0 disables the clamp (optimizer.py:76-86).  work_dev: device float32 [4]
  * scratch owned by the caller (zero-initialised once; the kernels leave it zeroed). */
 int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, float *g2_dev,
-                          int64_t count, float lr, float beta1, float beta2, int32_t step,
-                          float grad_limit, float *work_dev, void *stream);
+                          int64_t count, double lr, double beta1, double beta2, int32_t step,
+                          double grad_limit, float *work_dev, void *stream);
 
 #ifdef __cplusplus
 }

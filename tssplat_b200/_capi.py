@@ -60,7 +60,7 @@ def _load() -> C.CDLL:
     lib.tsb_grad_limit.restype = C.c_int
     lib.tsb_grad_limit.argtypes = [vp, i64, f32, f32, vp]
     lib.tsb_adam_uniform_step.restype = C.c_int
-    lib.tsb_adam_uniform_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, i32, f32, vp, vp]
+    lib.tsb_adam_uniform_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, i32, C.c_double, vp, vp]
     return lib
 
 

@@ -206,8 +206,8 @@ int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, v
   return TSB_OK;
 }
 
-int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, float *g2_dev, int64_t count, float lr,
-                          float beta1, float beta2, int32_t step, float grad_limit, float *work_dev, void *stream) {
+int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, float *g2_dev, int64_t count, double lr,
+                          double beta1, double beta2, int32_t step, double grad_limit, float *work_dev, void *stream) {
   if (!p_dev || !grad_dev || !g1_dev || !g2_dev || !work_dev || count < 0 || step < 1)
     return fail(nullptr, TSB_E_INVALID, "tsb_adam_uniform_step: null pointer, negative count or step < 1");
   if (count == 0) return TSB_OK;

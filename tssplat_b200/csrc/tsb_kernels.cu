@@ -470,12 +470,13 @@ __global__ void grad_limit_apply_kernel(float *g, int64_t count, float thr, floa
 
 // AdamUniform (utils/optimizer.py:37-89), pass 1: moments + the two global maxima.
 __global__ void adam_uniform_moments_kernel(const float *__restrict__ grad, float *__restrict__ g1, float *__restrict__ g2,
-                                            int64_t count, float b1, float b2, float inv_bc1, float inv_bc2, float *work) {
+                                            int64_t count, float b1, float b2, float omb1, float omb2, float inv_bc1,
+                                            float inv_bc2, float *work) {
   float mx2 = 0.f, mx1 = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
     const float g = grad[i];
-    const float m1 = b1 * g1[i] + (1.f - b1) * g;           // optimizer.py:61
-    const float m2 = b2 * g2[i] + (1.f - b2) * (g * g);     // optimizer.py:62
+    const float m1 = b1 * g1[i] + omb1 * g;                 // optimizer.py:61  (1 - beta formed in double on the host, like Python)
+    const float m2 = b2 * g2[i] + omb2 * (g * g);           // optimizer.py:62
     g1[i] = m1; g2[i] = m2;
     mx2 = fmaxf(mx2, sqrtf(m2 * inv_bc2));                  // optimizer.py:68,74
     mx1 = fmaxf(mx1, fabsf(m1 * inv_bc1));                  // optimizer.py:67,83
@@ -608,13 +609,15 @@ cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, float lr, float b1,
-                                float b2, int step, float grad_limit, float *work, cudaStream_t st) {
-  const float inv_bc1 = float(1.0 / (1.0 - pow(double(b1), double(step))));   // optimizer.py:67
-  const float inv_bc2 = float(1.0 / (1.0 - pow(double(b2), double(step))));   // optimizer.py:68
+cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, double lr, double b1,
+                                double b2, int step, double grad_limit, float *work, cudaStream_t st) {
+  const float inv_bc1 = float(1.0 / (1.0 - pow(b1, double(step))));   // optimizer.py:67
+  const float inv_bc2 = float(1.0 / (1.0 - pow(b2, double(step))));   // optimizer.py:68
   const int grid = grid_for(count, 256);
-  adam_uniform_moments_kernel<<<grid, 256, 0, st>>>(grad, g1, g2, count, b1, b2, inv_bc1, inv_bc2, work);
-  adam_uniform_apply_kernel<<<grid, 256, 0, st>>>(p, g1, count, lr, inv_bc1, grad_limit, work, reinterpret_cast<unsigned int *>(work + 2));
+  adam_uniform_moments_kernel<<<grid, 256, 0, st>>>(grad, g1, g2, count, float(b1), float(b2), float(1.0 - b1), float(1.0 - b2),
+                                                    inv_bc1, inv_bc2, work);
+  adam_uniform_apply_kernel<<<grid, 256, 0, st>>>(p, g1, count, float(lr), inv_bc1, float(grad_limit), work,
+                                                  reinterpret_cast<unsigned int *>(work + 2));
   return cudaGetLastError();
 }
 

@@ -41,7 +41,7 @@ void set_skip_combine(int v);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);
 cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st);
-cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, float lr,
-                                float b1, float b2, int step, float grad_limit, float *work2, cudaStream_t st);
+cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, double lr,
+                                double b1, double b2, int step, double grad_limit, float *work2, cudaStream_t st);
 
 }  // namespace tsb
