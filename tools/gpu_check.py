@@ -88,7 +88,7 @@ if __name__ == "__main__":
     t0 = time.time(); pack = make_pack(S, T, seed=0, unique=8); print(f"pack S={S} T={T}: n={pack.n} nele={pack.nele} ({time.time()-t0:.1f}s)")
     parity(pack, 512, 0.35, 2)
     if os.environ.get("QUICK"):
-        timing(pack, 512, 256); timing(pack, 512, 256, skip_combine=1)
+        timing(pack, 512, 256); timing(pack, 512, 256, skip_combine=1); timing(pack, 512, 512); timing(pack, 512, 512, skip_combine=1)
         sys.exit(0)
     for tt, nt in ((256, 256), (512, 256), (512, 512), (1024, 512)):
         timing(pack, tt, nt)
