@@ -85,6 +85,15 @@ int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int3
                     float gradH, const float *gradH_dev, float *energy_out_dev,
                     float *grad_out_dev, void *stream);
 
+/* Same computation for callers whose vertex positions live in HOST memory (e.g. a CPU-side
+ * optimiser): copies x_host -> device, runs the fused launch, copies energy[3] and grad back, all
+ * asynchronously on `stream`; the host buffers must stay valid until the stream has been
+ * synchronised (pinned memory makes the copies truly asynchronous).  grad_out_host may be NULL.
+ * Replaces the reference's implicit host round trips (the CPU scalar at tet_spheres_cuda.cu:194 and
+ * the caller's .cpu() of the gradient). */
+int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2, int32_t order,
+                         float gradH, float *energy_out_host, float *grad_out_host, void *stream);
+
 /* out = gradH * (*gradH_dev) * g  -- the cublasSscal at tet_spheres_cuda.cu:257-258 without the
  * .item() sync.  In-place allowed. */
 int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH_dev,

@@ -169,6 +169,26 @@ def test_autograd_surface(ext):
     assert ext.random_x(eng.tet_sp).shape == (pack.n, 3)
 
 
+def test_host_buffer_entry_point(ext):
+    """tsb_energy_grad_host: host x in, host energy/grad out, async on the current stream."""
+    pack = make_pack(3, 1024, seed=5)
+    x_np = perturb(pack, sigma_rel=0.35, seed=4)
+    sp = ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1))
+    x_host = torch.from_numpy(x_np).pin_memory()
+    g_host = torch.empty((pack.n, 3), dtype=torch.float32).pin_memory()
+    e_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    ext.energy_grad_host(sp, x_host, 1e-4, 2e-4, 4, 0.5, e_host, g_host)
+    torch.cuda.synchronize()
+    eo, terms, go = COracle(pack.verts, pack.tets).energy_grad(x_np, 1e-4, 2e-4, 4, gradH=0.5)
+    assert float(e_host[0]) == pytest.approx(eo, rel=REL) and float(e_host[2]) == pytest.approx(terms[1], rel=REL)
+    assert np.linalg.norm(g_host.numpy() - go) <= REL * np.linalg.norm(go)
+    ext.energy_grad_host(sp, x_host, 1e-4, 2e-4, 4, 0.5, e_host, None)          # energy only
+    torch.cuda.synchronize()
+    assert float(e_host[0]) == pytest.approx(eo, rel=REL)
+    with pytest.raises(RuntimeError):
+        ext.energy_grad_host(sp, x_host[:-1], 1e-4, 2e-4, 4, 0.5, e_host, g_host)
+
+
 def test_error_behaviour(ext):
     v, t = make_tet_sphere(1005, 128)
     sp = ext.TetSpheres(v.astype(np.float32).reshape(-1), t.reshape(-1))

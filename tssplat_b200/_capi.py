@@ -16,7 +16,7 @@ TSB_OK, TSB_E_INVALID, TSB_E_MESH, TSB_E_CUDA, TSB_E_NOMEM = 0, -1, -2, -3, -4
 
 # every symbol include/tssplat_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = (
-    "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_scale",
+    "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_energy_grad_host", "tsb_scale",
     "tsb_grad_limit", "tsb_adam_uniform_step",
 )
 
@@ -55,6 +55,8 @@ def _load() -> C.CDLL:
     lib.tsb_get_info.argtypes = [vp, C.POINTER(tsb_info_t)]
     lib.tsb_energy_grad.restype = C.c_int
     lib.tsb_energy_grad.argtypes = [vp, vp, f32, f32, i32, f32, vp, vp, vp, vp]
+    lib.tsb_energy_grad_host.restype = C.c_int
+    lib.tsb_energy_grad_host.argtypes = [vp, vp, f32, f32, i32, f32, vp, vp, vp]
     lib.tsb_scale.restype = C.c_int
     lib.tsb_scale.argtypes = [vp, i64, f32, vp, vp, vp]
     lib.tsb_grad_limit.restype = C.c_int

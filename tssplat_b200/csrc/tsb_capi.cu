@@ -17,6 +17,7 @@ struct tsb_handle_s {
   int device = 0;
   tsb::KParams kp{};
   const int32_t *slot_ptr = nullptr;
+  float *stage_x = nullptr, *stage_grad = nullptr, *stage_energy = nullptr;   // tsb_energy_grad_host staging
   tsb_info_t info{};
   std::vector<void *> allocs;
   std::string err;
@@ -173,6 +174,31 @@ int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int3
   kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
   cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, h->info.n, h->slot_ptr, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
+  return TSB_OK;
+}
+
+int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2, int32_t order, float gradH,
+                         float *energy_out_host, float *grad_out_host, void *stream) {
+  if (!h) return TSB_E_INVALID;
+  if (!x_host || !energy_out_host) return fail(h, TSB_E_INVALID, "x_host and energy_out_host must be non-null");
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(h, TSB_E_CUDA, "cannot select the handle's CUDA device");
+  const size_t nb = size_t(h->info.n) * 3 * sizeof(float);
+  if (!h->stage_x) {
+    int rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x);
+    if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_grad);
+    if (rc == TSB_OK) rc = alloc_zero(h, 4, &h->stage_energy);
+    if (rc != TSB_OK) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(h->stage_x, x_host, nb, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  const int rc = tsb_energy_grad(h, h->stage_x, c1, c2, order, gradH, nullptr, h->stage_energy,
+                                 grad_out_host ? h->stage_grad : nullptr, stream);
+  if (rc != TSB_OK) return rc;
+  e = cudaMemcpyAsync(energy_out_host, h->stage_energy, 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad, nb, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
 

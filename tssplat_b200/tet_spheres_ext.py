@@ -32,7 +32,7 @@ import torch
 from . import _capi
 from .mesh import load_veg
 
-__all__ = ["TetSpheres", "forward", "backward", "random_x", "grad_limit"]
+__all__ = ["TetSpheres", "forward", "backward", "random_x", "grad_limit", "energy_grad_host"]
 
 return_cpu_scalar = False
 #: compute the gradient inside ``forward`` (one launch per iteration) when ``x.requires_grad``
@@ -132,6 +132,22 @@ class TetSpheres:
         _capi.check(rc, self._h, "tet_spheres_ext")
         del keep
         return energy, grad
+
+
+def energy_grad_host(tet_sp: TetSpheres, x_host: torch.Tensor, c1: float, c2: float, order: int, gradH: float,
+                     energy_host: torch.Tensor, grad_host: Optional[torch.Tensor]) -> None:
+    """Host-buffer form of the fused launch (``tsb_energy_grad_host``): ``x_host`` [n,3] fp32 CPU
+    (ideally pinned) in, ``energy_host`` [3] and ``grad_host`` [n,3] CPU out, asynchronous on the
+    current stream -- synchronise the stream before reading the outputs."""
+    for t in (x_host, energy_host) + ((grad_host,) if grad_host is not None else ()):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("energy_grad_host needs contiguous float32 CPU tensors")
+    if x_host.numel() != tet_sp.n3 or energy_host.numel() < 3 or (grad_host is not None and grad_host.numel() != tet_sp.n3):
+        raise RuntimeError("energy_grad_host: wrong buffer sizes")
+    rc = _capi.lib.tsb_energy_grad_host(tet_sp._h, x_host.data_ptr(), float(c1), float(c2), int(order), float(gradH),
+                                        energy_host.data_ptr(), grad_host.data_ptr() if grad_host is not None else None,
+                                        _stream_ptr(tet_sp.device))
+    _capi.check(rc, tet_sp._h, "tet_spheres_ext.energy_grad_host")
 
 
 def _key(x: torch.Tensor, c1, c2, order):
