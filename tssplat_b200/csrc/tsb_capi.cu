@@ -290,6 +290,8 @@ void tsb_debug_plan_free(tsb_debug_plan_s *d) { delete d; }
 /* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
 void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
 void tsb_debug_set_skip_combine(int v) { tsb::set_skip_combine(v); }
+void tsb_debug_set_pdl_tile(int v) { tsb::set_pdl_tile(v); }
+void tsb_debug_set_exp_flags(int v) { tsb::set_exp_flags(v); }
 
 
 }  // extern "C"

@@ -82,6 +82,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
 int g_skip_combine = 0;   // developer switch (timing experiments only)
+int g_pdl_tile = 1;       // tile kernel launched with programmatic stream serialisation
+int g_exp_flags = 0;
 
 
 
@@ -311,6 +313,11 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     if (n_my > 0) { issue_v(0); issue_t(0); }
   }
   if (WITH_GRAD && tid < 3) outb[tid * TTP + TT] = 0.f;   // zero column for gather-table padding
+  // Everything above touches only plan data.  x (may have been updated by the optimiser), the scratch
+  // slots and the energy partials belong to the previous kernels in the stream: wait for them here.
+  // (The kernel is launched with programmatic stream serialisation, so this prologue overlaps the
+  // tail of the previous combine kernel.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (n_my > 0) load_x(vid, px);
   __syncthreads();
 
@@ -357,12 +364,17 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     if (WITH_GRAD) {
       mbar_wait(&bar_e, j & 1);
       float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-      for (int r = tid; r < nrow; r += NT) {
-        const int g = r >> 5, lane = r & 31;
-        const int beg = grp_s[g], end = grp_s[g + 1];
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
-        scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
+      // rows are sorted longest first; alternate the direction of successive passes ("snake") so the
+      // warp that got the longest rows of one pass gets the shortest of the next
+      for (int q = 0; q * NT < nrow; ++q) {
+        const int r = q * NT + (((q & 1) && !(p.exp_flags & 1)) ? (NT - 1 - tid) : tid);
+        if (r < nrow) {
+          const int g = r >> 5, lane = r & 31;
+          const int beg = grp_s[g], end = grp_s[g + 1];
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+          gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
+          scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
+        }
       }
     }
   }
@@ -390,9 +402,10 @@ __global__ void __launch_bounds__(NT) combine_kernel(const __grid_constant__ KPa
   const int v = blockIdx.x * NT + tid;
   int s0 = 0, s1 = 0;
   if (v < n_vertices) { s0 = __ldg(slot_ptr + v); s1 = __ldg(slot_ptr + v + 1); }   // plan data: safe before the wait
-  float gh = p.gradH;
-  if (p.gradH_dev) gh *= __ldg(p.gradH_dev);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next tile kernel may start its prologue
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  float gh = p.gradH;
+  if (p.gradH_dev) gh *= __ldg(p.gradH_dev);   // produced by earlier kernels in the stream: read after the wait
   if (v < n_vertices) {
     const float4 *scratch4 = reinterpret_cast<const float4 *>(p.scratch);
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -513,13 +526,22 @@ int g_num_sms = 148;
 template <int TT, int NV, int NT, int MINB>
 cudaError_t launch_variant(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
   KParams p = p0;
+  p.exp_flags = g_exp_flags;
   const int slots = MINB * g_num_sms;
   const int grid = p.n_tiles < slots ? p.n_tiles : slots;
   p.n_energy = grid;
-  const int smem = Smem<TT, NV>::kBytes;
-  if (p.grad) energy_grad_kernel<TT, NV, NT, MINB, true><<<grid, NT, smem, stream>>>(p);
-  else energy_grad_kernel<TT, NV, NT, MINB, false><<<grid, NT, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = Smem<TT, NV>::kBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_tile ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = p.grad ? cudaLaunchKernelEx(&cfg, energy_grad_kernel<TT, NV, NT, MINB, true>, p)
+                         : cudaLaunchKernelEx(&cfg, energy_grad_kernel<TT, NV, NT, MINB, false>, p);
   if (e != cudaSuccess || g_skip_combine) return e;
   return launch_combine(p, n_vertices, slot_ptr, stream);
 }
@@ -596,6 +618,8 @@ cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, 
 
 void set_threads_512(int nt) { g_threads_512 = (nt == 512) ? 512 : 256; }
 void set_skip_combine(int v) { g_skip_combine = v; }
+void set_pdl_tile(int v) { g_pdl_tile = v; }
+void set_exp_flags(int v) { g_exp_flags = v; }
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s) {
   scale_kernel<<<grid_for(count, 256), 256, 0, s>>>(g, count, gradH, gradH_dev, out);

@@ -28,6 +28,7 @@ struct KParams {
   int32_t n_tiles;
   int32_t n_energy;             // number of (smooth, barrier) partials the tile kernel writes
   int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
+  int32_t exp_flags;            // developer A/B switches (0 in production)
 };
 
 // Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
@@ -38,6 +39,8 @@ int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled vari
 
 void set_threads_512(int nt);
 void set_skip_combine(int v);
+void set_pdl_tile(int v);
+void set_exp_flags(int v);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);
 cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st);
