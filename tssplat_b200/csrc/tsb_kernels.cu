@@ -364,17 +364,12 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     if (WITH_GRAD) {
       mbar_wait(&bar_e, j & 1);
       float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-      // rows are sorted longest first; alternate the direction of successive passes ("snake") so the
-      // warp that got the longest rows of one pass gets the shortest of the next
-      for (int q = 0; q * NT < nrow; ++q) {
-        const int r = q * NT + (((q & 1) && !(p.exp_flags & 1)) ? (NT - 1 - tid) : tid);
-        if (r < nrow) {
-          const int g = r >> 5, lane = r & 31;
-          const int beg = grp_s[g], end = grp_s[g + 1];
-          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-          gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
-          scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
-        }
+      for (int r = tid; r < nrow; r += NT) {
+        const int g = r >> 5, lane = r & 31;
+        const int beg = grp_s[g], end = grp_s[g + 1];
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
+        scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
       }
     }
   }
