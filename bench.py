@@ -171,6 +171,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tile-tets", type=int, default=0)
+    ap.add_argument("--spheres-per-gpu", type=int, default=SPHERES,
+                    help="weak scaling (default): spheres owned by every rank")
+    ap.add_argument("--total-spheres", type=int, default=0,
+                    help="strong scaling: total spheres split sphere-per-rank (BASELINE configs[3], [4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -196,11 +200,20 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs: R distinct 64-sphere packs per rank, resident in HBM ----------------------------
-    c1, c2 = 2e-4 / SPHERES, 2e-4
+    # ---- inputs: R distinct packs per rank, resident in HBM ---------------------------------------
+    strong = args.total_spheres > 0
+    if strong:
+        from tssplat_b200.sharding import partition_spheres
+        lo, hi = partition_spheres([TETS] * args.total_spheres, world)[rank]
+        n_sph = hi - lo
+    else:
+        n_sph = args.spheres_per_gpu
+    total_spheres = args.total_spheres if strong else n_sph * world
+    c1, c2 = 2e-4 / total_spheres, 2e-4
     packs, handles, xs = [], [], []
-    for i in range(N_ROTATE):
-        pk = make_pack(SPHERES, TETS, seed=1000 * rank + 17 * i, unique=8)
+    n_rotate = N_ROTATE if n_sph <= 128 else max(2, N_ROTATE * 64 // n_sph)
+    for i in range(n_rotate):
+        pk = make_pack(n_sph, TETS, seed=1000 * rank + 17 * i, unique=8)
         packs.append(pk)
         handles.append(ext.TetSpheres(pk.verts.reshape(-1), pk.tets.reshape(-1), tile_tets=args.tile_tets))
         xs.append(torch.from_numpy(perturb(pk, sigma_rel=0.02, seed=i)).to(dev))
@@ -208,7 +221,7 @@ def main():
     info = handles[0].info
     b_alg = float(np.mean([pk.algorithmic_bytes() for pk in packs]))
     footprint = sum(h.info["stream_bytes"] for h in handles)
-    energies = torch.zeros((N_ROTATE, 3), device=dev)
+    energies = torch.zeros((n_rotate, 3), device=dev)
     grads = [torch.empty((h.n, 3), device=dev) for h in handles]
     stream = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev)
@@ -222,18 +235,18 @@ def main():
 
     with torch.cuda.stream(stream):
         for w in range(args.warmup):
-            launch(w % N_ROTATE, stream.cuda_stream)
+            launch(w % n_rotate, stream.cuda_stream)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            for i in range(N_ROTATE):
+            for i in range(n_rotate):
                 launch(i, stream.cuda_stream)
         graph.replay()
         stream.synchronize()
 
     def timed_region(steps, rotate=True):
         """Exactly `steps` steps; returns seconds (device time, this rank)."""
-        reps, rem = divmod(steps, N_ROTATE)
+        reps, rem = divmod(steps, n_rotate)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
@@ -255,7 +268,7 @@ def main():
             dist.barrier()
         return ev0.elapsed_time(ev1) * 1e-3
 
-    timed_region(min(args.steps, 10 * N_ROTATE))                      # settle clocks / NCCL
+    timed_region(min(args.steps, 10 * n_rotate))                      # settle clocks / NCCL
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_local = timed_region(args.steps)
@@ -265,22 +278,24 @@ def main():
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     t = float(t_all.item())
     ms_per_step = t / args.steps * 1e3
-    value = world * args.steps / t
+    # weak: every rank steps its own pack -> aggregate pack-iterations/s; strong: all ranks together
+    # advance ONE pack of total_spheres per step.  Reported in units of the 64-sphere metric pack.
+    value = args.steps / t * (total_spheres / SPHERES)
 
     # ---- warm-L2 variant (one pack replayed): explains the launch-latency floor ---------------
     with torch.cuda.stream(stream):
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1, stream=stream):
-            for _ in range(N_ROTATE):
+            for _ in range(n_rotate):
                 launch(0, stream.cuda_stream)
         g1.replay(); stream.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(max(1, args.steps // N_ROTATE)):
+        for _ in range(max(1, args.steps // n_rotate)):
             g1.replay()
         e1.record(stream)
         stream.synchronize()
-    warm_ms = e0.elapsed_time(e1) / (max(1, args.steps // N_ROTATE) * N_ROTATE)
+    warm_ms = e0.elapsed_time(e1) / (max(1, args.steps // n_rotate) * n_rotate)
 
     # ---- end to end with HOST buffers: (1) through the C-ABI host entry point, (2) through the
     # reference-facing autograd surface (SmoothnessBarrierEnergy) -- copies inside the timed region
@@ -305,8 +320,9 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return world * steps / float(te.item())
 
+    e2e_scale = (n_sph / SPHERES) if not strong else (total_spheres / SPHERES) / world
     e2e_steps = int(min(args.steps, 500))
-    e2e_value = timed_e2e(lambda: ext.energy_grad_host(handles[0], x_host, c1, c2, ORDER, 1.0, e_host, g_host), e2e_steps)
+    e2e_value = e2e_scale * timed_e2e(lambda: ext.energy_grad_host(handles[0], x_host, c1, c2, ORDER, 1.0, e_host, g_host), e2e_steps)
 
     eng = SmoothnessBarrierEnergy.__new__(SmoothnessBarrierEnergy)
     torch.nn.Module.__init__(eng)
@@ -326,22 +342,23 @@ def main():
         g_host.copy_(tet_v.grad, non_blocking=True)                  # D2H of the result
         e0_host.copy_(e.detach(), non_blocking=True)
 
-    e2e_autograd = timed_e2e(autograd_step, int(min(args.steps, 300)))
+    e2e_autograd = e2e_scale * timed_e2e(autograd_step, int(min(args.steps, 300)))
 
     if rank == 0:
         peak, peak_src = _peaks()
         achieved = b_alg / (t / args.steps) / 1e9                   # GB/s per GPU, whole step (both launches)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{SPHERES} tet-spheres x {TETS} tets per GPU, fused energy+grad (tile kernel + "
-                                   "combine kernel); kernel-only form of BASELINE configs[2] (rasterizer deps absent)",
-                       "spheres_per_gpu": SPHERES, "tets_per_sphere": TETS, "vertices": int(n), "order": ORDER,
+            "config": {"workload": f"{n_sph} tet-spheres x {TETS} tets per GPU ({total_spheres} in total), fused energy+grad "
+                                   "(tile kernel + combine kernel); kernel-only form of BASELINE configs[2] (rasterizer "
+                                   "deps absent); value is in 64-sphere-pack iterations/s",
+                       "spheres_per_gpu": n_sph, "total_spheres": total_spheres, "tets_per_sphere": TETS, "vertices": int(n), "order": ORDER,
                        "x": "rest + N(0,(0.02 h)^2), no inverted tets", "parallelism": f"sphere-per-rank x{world}",
-                       "l2": f"inputs larger than L2: rotating {N_ROTATE} distinct packs, {footprint / 1e6:.0f} MB "
+                       "l2": f"inputs larger than L2: rotating {n_rotate} distinct packs, {footprint / 1e6:.0f} MB "
                              "of per-step data > 126 MB L2", "tile_tets": int(info["tile_tets"]),
-                       "tiles": int(info["n_tiles"]), "graph": f"CUDA graph of {N_ROTATE} steps replayed"},
+                       "tiles": int(info["n_tiles"]), "graph": f"CUDA graph of {n_rotate} steps replayed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_step": b_alg,
@@ -357,7 +374,7 @@ def main():
                        "warm_l2_ms_per_step": warm_ms, "warm_l2_iters_per_s": 1e3 / warm_ms,
                        "stream_bytes_per_step": int(info["stream_bytes"])},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and n_sph == SPHERES:
             cores = os.cpu_count() or 1
             x0 = xs[0].cpu().numpy()
             co = _c_oracle(packs[0])

@@ -147,3 +147,24 @@ def test_oracle_reproduces_golden(aveg):
             assert terms[0] == pytest.approx(float(gold[k + "/smooth"]), rel=1e-10)
             assert np.linalg.norm(g) == pytest.approx(float(gold[k + "/grad_l2"]), rel=1e-10)
             assert np.abs(g[:: max(1, len(g) // 64)][:64] - gold[k + "/grad_sample"]).max() <= 1e-9 * np.abs(g).max()
+
+
+def test_vanilla_pytorch_restatement_single_sphere():
+    """BASELINE.json configs[0]: one tet-sphere, vanilla-PyTorch energy fwd+bwd on the CPU
+    (oracle/torch_energy.py: torch sparse fp32 + autograd following the reference's SpMV pipeline)
+    against the fp64 oracle.  Loose tolerance on purpose: the fp32 x^T M x form is the reference's own
+    arithmetic and loses digits near the rest state."""
+    import torch
+    from oracle.torch_energy import TorchEnergy
+    v, t = make_tet_sphere(1000, 4096)
+    v = v.astype(np.float32)
+    x_np = perturb(v, t, 0.35, 1)
+    mod = TorchEnergy(v, t)
+    x = torch.from_numpy(x_np).clone().requires_grad_(True)
+    for order in (2, 4):
+        x.grad = None
+        e = mod(x, 2e-4, 2e-4, order)
+        e.backward()
+        eo, _, go = COracle(v, t).energy_grad(x_np, 2e-4, 2e-4, order)
+        assert float(e) == pytest.approx(eo, rel=2e-4)
+        assert np.linalg.norm(x.grad.numpy() - go) <= 2e-3 * np.linalg.norm(go)
