@@ -211,12 +211,18 @@ def main():
     total_spheres = args.total_spheres if strong else n_sph * world
     c1, c2 = 2e-4 / total_spheres, 2e-4
     packs, handles, xs = [], [], []
-    n_rotate = N_ROTATE if n_sph <= 128 else max(2, N_ROTATE * 64 // n_sph)
-    for i in range(n_rotate):
+    L2_BYTES = 126e6
+    n_rotate = None
+    i = 0
+    while n_rotate is None or i < n_rotate:
         pk = make_pack(n_sph, TETS, seed=1000 * rank + 17 * i, unique=8)
         packs.append(pk)
         handles.append(ext.TetSpheres(pk.verts.reshape(-1), pk.tets.reshape(-1), tile_tets=args.tile_tets))
         xs.append(torch.from_numpy(perturb(pk, sigma_rel=0.02, seed=i)).to(dev))
+        if n_rotate is None:   # enough distinct packs that one rotation streams > 1.5 x L2 through the GPU
+            n_rotate = int(min(64, max(2, -(-1.5 * L2_BYTES // handles[0].info["stream_bytes"]))))
+            n_rotate = max(n_rotate, N_ROTATE if n_sph <= 128 else 2)
+        i += 1
     n = handles[0].n
     info = handles[0].info
     b_alg = float(np.mean([pk.algorithmic_bytes() for pk in packs]))
