@@ -269,3 +269,39 @@ def test_grad_limit_and_adam_uniform(ext):
     assert torch.allclose(p, p_ref, rtol=1e-5, atol=1e-7) and torch.allclose(g1, g1r, rtol=1e-5, atol=1e-6)
     assert torch.allclose(g2, g2r, rtol=1e-5, atol=1e-8)
     assert torch.all(work == 0)
+
+
+def test_adam_uniform_optimizer_class(ext):
+    """tssplat_b200.optimizer.AdamUniform (drop-in for utils/optimizer.py) against a torch restatement
+    of the reference's step, incl. the grad_limit schedule, and a short energy-only descent."""
+    from tssplat_b200.optimizer import AdamUniform
+    torch.manual_seed(1)
+    p = torch.nn.Parameter(torch.randn(2000, 3, device="cuda"))
+    ref = p.detach().clone()
+    g1r, g2r = torch.zeros_like(ref), torch.zeros_like(ref)
+    opt = AdamUniform([p], grad_limit=True, grad_limit_values=[0.05, 0.01], grad_limit_iters=[3], lr=0.2)
+    lr, b1, b2 = 0.2, 0.9, 0.999
+    ptr, cc = 0, 0
+    for step in range(1, 7):
+        grad = torch.randn_like(ref) * (5.0 if step % 2 else 0.01)
+        p.grad = grad.clone()
+        opt.step()
+        g1r.mul_(b1).add_(grad, alpha=1 - b1)
+        g2r.mul_(b2).add_(grad.square(), alpha=1 - b2)
+        gr = (g1r / (1 - b1 ** step)) / (1e-8 + (g2r / (1 - b2 ** step)).sqrt().max())
+        m = [0.05, 0.01][ptr]
+        if ptr < 1 and cc >= 3:
+            ptr += 1
+        s = gr.abs().max()
+        if s > m:
+            gr = gr * (m / s)
+        ref.sub_(gr, alpha=lr)
+        cc += 1
+    torch.cuda.synchronize()
+    assert torch.allclose(p.detach(), ref, rtol=1e-5, atol=1e-6)
+    # descent: the loop the trainer runs around the energy must decrease it
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from energy_only_loop import run
+    rate, e0, e1 = run(spheres=2, iters=60)
+    assert e1 < 0.5 * e0 and np.isfinite(e1)
