@@ -286,11 +286,13 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &bar_t);
     bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t);
   };
-  auto issue_e = [&](int j) {
-    const int2 el = __ldg(p.tile_ell + int(blockIdx.x) + j * G);
+  auto issue_e = [&](const int2 el) {
     mbar_expect_tx(&bar_e, 2u * uint32_t(el.y));
     if (el.y > 0) bulk_g2s(smem_raw + L::kEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e);
   };
+  // TMA is issued by the LAST thread: its warp processes the fewest tets of a tile, so the issue
+  // latency stays off the critical path of the tet math.
+  const bool issuer = (tid == NT - 1);
   auto load_vids = [&](int j, int (&vid)[kVPer]) {     // entries past nvert are zero padding (-> x[0])
     const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(int(blockIdx.x) + j * G) * L::kVBytes + 64);
 #pragma unroll
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
   int vid[kVPer];
   float px[kVPer][3];
   if (n_my > 0) load_vids(0, vid);
-  if (tid == 0) {
+  if (issuer) {
     mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1); mbar_init(&bar_t, 1); mbar_init(&bar_e, 1);
     mbar_fence_init();
     if (n_my > 0) { issue_v(0); issue_t(0); }
@@ -333,6 +335,8 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
     const int32_t *slot_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV);
     const int32_t *grp_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV + 4 * NR);
     if (j + 1 < n_my) load_vids(j + 1, vid);           // ids of the next tile: needed only after this tile's tet math
+    int2 el = make_int2(0, 0);
+    if (WITH_GRAD && issuer) el = __ldg(p.tile_ell + int(blockIdx.x) + j * G);   // consumed after (A): latency hidden
 
     // ---------------- phase 0: x (already in registers) + rest X -> shared -------------------
     mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
@@ -343,9 +347,9 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
       if (i < nvert) xs4[i] = make_float4(px[q][0], px[q][1], px[q][2], Xx_s[i]);
     }
     __syncthreads();     // (A) xs4 complete; every thread has left the previous tile's row gather
-    if (tid == 0) {
+    if (issuer) {
       if (j + 1 < n_my) issue_v(j + 1);               // its stage held tile j-1, now fully consumed
-      if (WITH_GRAD) issue_e(j);                       // gather-table buffer is free since (A)
+      if (WITH_GRAD) issue_e(el);                      // gather-table buffer is free since (A)
     }
 
     // ---------------- phase 1: tets -----------------------------------------------------------------
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_cons
       tet_body<TTP, WITH_GRAD>(lt, idx_s, B_s, xs4, xs2, outb, c1, c2, order, lscale, es, eb);
     __syncthreads();     // (B) output table complete; tet blob and xs4 are free
     if (j + 1 < n_my) {
-      if (tid == 0) issue_t(j + 1);
+      if (issuer) issue_t(j + 1);
       load_x(vid, px);                                 // lands while the row gather below runs
     } else {
       asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // last tile: let the combine kernel launch
