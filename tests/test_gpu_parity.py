@@ -235,6 +235,22 @@ def test_full_size_properties_64_spheres(ext):
     assert np.linalg.norm(gs.cpu().numpy() - g[v0:v1]) <= 2e-5 * np.linalg.norm(g[v0:v1])
 
 
+def test_large_pack_properties_256_spheres(ext):
+    """BASELINE configs[3] size on one GPU (256 spheres, 1.05 M tets): parity with the C oracle and
+    the oracle-free invariants, on a pack where every persistent CTA loops over ~7 tiles."""
+    pack = make_pack(256, 4096, seed=3, unique=8)
+    x_np = perturb(pack, sigma_rel=0.35, seed=2)
+    c1, c2 = 2e-4 / 256, 2e-4
+    sp, e, g = _check(ext, pack.verts, pack.tets, x_np, c1, c2, 4)
+    assert sp.info["n_tiles"] > 4 * 296
+    x2 = torch.from_numpy(x_np).cuda()
+    e2, g2 = sp.energy_grad(x2, c1, c2, 4)
+    assert torch.equal(torch.from_numpy(g.astype(np.float32)).cuda(), g2)       # bitwise repeatable
+    forces = np.add.reduceat(g, pack.vert_offsets[:-1].astype(np.int64), axis=0)  # net force per sphere
+    scale = np.add.reduceat(np.abs(g), pack.vert_offsets[:-1].astype(np.int64), axis=0)
+    assert np.all(np.abs(forces) <= 3e-4 * scale.max(axis=1, keepdims=True))
+
+
 def test_grad_limit_and_adam_uniform(ext):
     from tssplat_b200 import _capi
     torch.manual_seed(0)
