@@ -147,7 +147,7 @@ def test_autograd_surface(ext):
         loss.backward()
         order = 4 if it > 1000 else 2
         eo, _, go = orc.energy_grad(x_np, c1, c2, order, gradH=3.0)
-        assert float(e) == pytest.approx(eo, rel=REL)
+        assert float(e.detach()) == pytest.approx(eo, rel=REL)
         g = tet_v.grad.cpu().numpy().astype(np.float64)
         assert tet_v.grad.shape == (pack.n, 3) and np.linalg.norm(g - go) <= REL * np.linalg.norm(go)
     # stale-cache protection: modify x in place between forward and backward -> backward recomputes
@@ -187,6 +187,21 @@ def test_host_buffer_entry_point(ext):
     assert float(e_host[0]) == pytest.approx(eo, rel=REL)
     with pytest.raises(RuntimeError):
         ext.energy_grad_host(sp, x_host[:-1], 1e-4, 2e-4, 4, 0.5, e_host, g_host)
+
+
+def test_construct_from_veg_file(ext, tmp_path):
+    """TetSpheres(filename) (tet_spheres.cpp:108-117,233) without libpgo: the .veg reader feeds tsb_create."""
+    from tssplat_b200.mesh import save_veg
+    v, t = make_tet_sphere(1007, 300)
+    path = str(tmp_path / "sphere.veg")
+    save_veg(path, v, t)
+    sp = ext.TetSpheres(path)
+    assert sp.n == len(v) and sp.nele == len(t)
+    x_np = perturb(v, t, 0.3, 2)
+    e, g = sp.energy_grad(torch.from_numpy(x_np).cuda(), 1e-3, 1e-3, 2)
+    eo, _, go = COracle(v.astype(np.float32), t).energy_grad(x_np, 1e-3, 1e-3, 2)
+    assert float(e[0]) == pytest.approx(eo, rel=REL)
+    assert np.linalg.norm(g.cpu().numpy() - go) <= REL * np.linalg.norm(go)
 
 
 def test_error_behaviour(ext):
