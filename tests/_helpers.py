@@ -196,7 +196,7 @@ def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
         for r in range(nrow):
             g, lane = r >> 5, r & 31
             blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32, 2).astype(np.int64)
-            assert blk.shape[0] * 2 <= 2 * ROW_CAP        # columns: at most twice the row cap (coloured rows have holes)
+            assert blk.shape[0] * 2 <= ROW_CAP
             ent = blk[:, lane, :].reshape(-1)
             n_real += int((ent != TT).sum())
             sl = int(td["slot"][r])

@@ -88,12 +88,13 @@ if __name__ == "__main__":
     t0 = time.time(); pack = make_pack(S, T, seed=0, unique=8); print(f"pack S={S} T={T}: n={pack.n} nele={pack.nele} ({time.time()-t0:.1f}s)")
     parity(pack, 512, 0.35, 2)
     if os.environ.get("QUICK"):
+        import ctypes
+        from tssplat_b200 import _capi
         for rep in range(2):
-            for mode in ("1", "0"):
-                os.environ["TSSPLAT_B200_COLOUR_ROWS"] = mode
-                print(f"  colour_rows={mode}")
+            for fl in (0, 1):
+                _capi.lib.tsb_debug_set_exp_flags(ctypes.c_int(fl)); print(f"  exp_flags={fl}")
                 timing(pack, 512, 256); timing(pack, 512, 256, skip_combine=1)
-        os.environ.pop("TSSPLAT_B200_COLOUR_ROWS")
+        _capi.lib.tsb_debug_set_exp_flags(ctypes.c_int(0))
         sys.exit(0)
     for tt, nt in ((256, 256), (512, 256), (512, 512), (1024, 512)):
         timing(pack, tt, nt)

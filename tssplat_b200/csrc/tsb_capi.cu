@@ -100,7 +100,6 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) po.balance_sms = sms;
     if (const char *env = std::getenv("TSSPLAT_B200_BALANCE")) po.balance_sms = std::atoi(env) ? po.balance_sms : 0;
-    if (const char *env = std::getenv("TSSPLAT_B200_COLOUR_ROWS")) po.colour_rows = std::atoi(env);
   }
 
   tsb::HostPlan plan;
@@ -257,7 +256,6 @@ int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, 
   po.laplacian_scale = laplacian_scale;
   po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
   if (po.max_local_vertices == 0) return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets");
-  if (const char *env = std::getenv("TSSPLAT_B200_COLOUR_ROWS")) po.colour_rows = std::atoi(env);
   po.balance_sms = balance_sms;
   tsb_debug_plan_s *d = new tsb_debug_plan_s();
   std::string err;

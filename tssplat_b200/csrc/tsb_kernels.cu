@@ -90,7 +90,7 @@ int g_exp_flags = 0;
 template <int TT, int NV>
 struct Smem {
   static constexpr int NR = NV + 8 * TT / kRowCap;           // == rows_cap(TT, NV)
-  static constexpr int ELLCAP = 12 * TT + 32 * kRowCap + NR + 64;  // == ell_cap(TT, NV)
+  static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;   // == ell_cap(TT, NV)
   static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
   static constexpr int kVStage = align_up(kVBytes, 128);     // two vertex-blob stages
   static constexpr int kTOff = 2 * kVStage;

@@ -334,7 +334,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
   struct Row { int32_t vert, chunk, len; };
   std::vector<Row> rows;
-  std::vector<int32_t> grp_rel, fill_cnt, row_n, grp_cols;
+  std::vector<int32_t> grp_rel, fill_cnt, row_n;
   std::vector<uint16_t> row_ent;
   for (int tile = 0; tile < NTILE; ++tile) {
     const std::vector<int32_t> &vs = tile_verts[tile];
@@ -363,7 +363,17 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     const int nrow = int(rows.size());
     if (nrow > NR) { err = "internal: gather-table rows exceed capacity"; return TSB_E_INVALID; }
     const int ngrp = (nrow + 31) / 32;
-    // row index of (vertex, chunk); chunks of a vertex are NOT adjacent after sorting
+    grp_rel.assign(size_t(ngrp) + 1, 0);
+    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * ((rows[size_t(g) * 32].len + 1) & ~1);
+    const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
+    if (nell > ell_cap(TT, NVMAX)) { err = "internal: gather table exceeds capacity"; return TSB_E_INVALID; }
+    while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
+    if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
+    hd->ntet = ntet; hd->nvert = nv; hd->nrow = nrow; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
+    P.tile_ell.push_back(hd->ell_off); P.tile_ell.push_back(nell);
+    for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
+    P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
+    // row index of (vertex, chunk 0); chunks of a vertex are NOT adjacent after sorting, so map each
     std::vector<std::vector<int32_t>> row_of(nv);
     for (int r = 0; r < nrow; ++r) {
       std::vector<int32_t> &ro = row_of[rows[r].vert];
@@ -383,111 +393,40 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
         row_ent[size_t(r) * kRowCap + row_n[r]++] = uint16_t(s * 3 * TTP + lt);
       }
     }
-    // Columns per 32-row group.  A warp-wide table load is conflict-free when its 32 lanes hit 32
-    // distinct banks (bank = word offset mod 32; the three components are +TTP words apart, i.e. the
-    // same permutation shifted) -- lanes that read padding all read the same zero word (broadcast).
-    // With C = max(longest row, busiest bank) columns a proper edge colouring of the bipartite
-    // multigraph (lanes x banks, one edge per entry) exists (Koenig), i.e. every column is
-    // conflict-free; rows then contain holes.  C is capped (a pathological bank would otherwise
-    // blow the table up) and the whole tile falls back to dense rows if the staged table would not
-    // fit: then conflicts are only reduced greedily.
-    const int kColCap = 2 * kRowCap;
-    grp_cols.assign(ngrp, 0);
-    bool coloured = opt.colour_rows != 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      grp_rel.assign(size_t(ngrp) + 1, 0);
-      for (int g = 0; g < ngrp; ++g) {
-        const int r0 = g * 32, r1 = std::min(nrow, r0 + 32);
-        int cols = rows[size_t(r0)].len;
-        if (coloured) {
-          int bankdeg[32] = {};
-          for (int r = r0; r < r1; ++r)
-            for (int e = 0; e < row_n[r]; ++e) bankdeg[row_ent[size_t(r) * kRowCap + e] & 31]++;
-          for (int bnk = 0; bnk < 32; ++bnk) cols = std::max(cols, bankdeg[bnk]);
-          cols = std::min(cols, kColCap);
-        }
-        grp_cols[g] = (cols + 1) & ~1;
-        grp_rel[g + 1] = grp_rel[g] + 32 * grp_cols[g];
-      }
-      if (!coloured || ((grp_rel[ngrp] + 7) / 8) * 8 <= ell_cap(TT, NVMAX)) break;
-      coloured = false;   // does not fit the staged table: dense rows
-    }
-    const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
-    if (nell > ell_cap(TT, NVMAX)) { err = "internal: gather table exceeds capacity"; return TSB_E_INVALID; }
-    while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
-    if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
-    hd->ntet = ntet; hd->nvert = nv; hd->nrow = nrow; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
-    P.tile_ell.push_back(hd->ell_off); P.tile_ell.push_back(nell);
-    for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
-    P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
+    // Order the entries of the 32 rows of a group so that, column by column, the 32 lanes of the
+    // warp read distinct shared-memory banks (bank = word offset mod 32; the three components
+    // are +TTP words apart, i.e. the same permutation shifted).  Greedy column-by-column
+    // matching, rows with the fewest remaining entries first within a column.
     for (int g = 0; g < ngrp; ++g) {
       const int r0 = g * 32, r1 = std::min(nrow, r0 + 32);
-      const int C = grp_cols[g];
+      const int glen = (grp_rel[g + 1] - grp_rel[g]) / 32;
       const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
-      auto put = [&](int lane, int col, uint16_t v) { P.ell[base + size_t(col >> 1) * 64 + size_t(lane) * 2 + (col & 1)] = v; };
-      // lane_col[l][c] / bank_col[b][c]: entry (row-local index e of lane l, as l*kRowCap+e) or -1
-      int16_t lane_col[32][2 * kRowCap], bank_col[32][2 * kRowCap];
-      for (int i = 0; i < 32; ++i)
-        for (int c = 0; c < C; ++c) { lane_col[i][c] = -1; bank_col[i][c] = -1; }
-      auto ent_of = [&](int id) { return row_ent[size_t(r0 + id / kRowCap) * kRowCap + id % kRowCap]; };
-      for (int r = r0; r < r1; ++r) {
-        const int l = r - r0;
-        for (int e = 0; e < row_n[r]; ++e) {
-          const int id = l * kRowCap + e, bnk = ent_of(id) & 31;
-          int ca = -1, cb = -1;
-          for (int c = 0; c < C && ca < 0; ++c) if (lane_col[l][c] < 0) ca = c;      // always exists: row_n <= C
-          if (coloured) for (int c = 0; c < C && cb < 0; ++c) if (bank_col[bnk][c] < 0) cb = c;
-          if (!coloured || cb < 0) {
-            // dense rows (or a bank busier than the cap): least-loaded free column of this lane
-            int best = -1, best_load = 1 << 30;
-            for (int c = 0; c < C; ++c) {
-              if (lane_col[l][c] >= 0) continue;
-              int load = 0;
-              for (int q = 0; q < 32; ++q) if (lane_col[q][c] >= 0 && (ent_of(lane_col[q][c]) & 31) == bnk) ++load;
-              if (!coloured && c >= rows[size_t(r0)].len) continue;
-              if (load < best_load) { best_load = load; best = c; }
-            }
-            if (best < 0) best = ca;
-            lane_col[l][best] = int16_t(id);
-            if (bank_col[bnk][best] < 0) bank_col[bnk][best] = int16_t(id);
-            continue;
+      uint8_t used_e[32][kRowCap] = {};
+      for (int k = 0; k < glen; ++k) {
+        uint32_t bank_used = 0;
+        // two passes: first place rows that can take a free bank, then the rest
+        int pending[32], np = 0;
+        for (int r = r0; r < r1; ++r) {
+          if (k >= row_n[r]) continue;   // this row is already exhausted -> padding (zero column)
+          int pick = -1;
+          for (int e = 0; e < row_n[r]; ++e) {
+            if (used_e[r - r0][e]) continue;
+            const int bank = row_ent[size_t(r) * kRowCap + e] & 31;
+            if (!(bank_used >> bank & 1u)) { pick = e; break; }
           }
-          if (lane_col[l][cb] >= 0) {
-            // colour cb is free at the bank but taken at the lane; ca is free at the lane but taken at
-            // the bank: flip the ca/cb alternating path that starts at the bank, then ca is free at both
-            int cur_bank = bnk, c_from = ca, c_to = cb;
-            // walk: bank --c_from--> lane --c_to--> bank --c_from--> ...
-            int path[128], np = 0;
-            int x = bank_col[cur_bank][c_from];
-            while (x >= 0 && np < 126) {
-              path[np++] = x;
-              const int ln = x / kRowCap;
-              const int y = lane_col[ln][c_to];
-              if (y < 0) break;
-              path[np++] = y;
-              cur_bank = ent_of(y) & 31;
-              x = bank_col[cur_bank][c_from];
-            }
-            // un-assign the path, then re-assign with swapped colours
-            for (int i = 0; i < np; ++i) {
-              const int id2 = path[i], c_old = (i & 1) ? c_to : c_from;
-              lane_col[id2 / kRowCap][c_old] = -1;
-              bank_col[ent_of(id2) & 31][c_old] = -1;
-            }
-            for (int i = 0; i < np; ++i) {
-              const int id2 = path[i], c_new = (i & 1) ? c_from : c_to;
-              lane_col[id2 / kRowCap][c_new] = int16_t(id2);
-              bank_col[ent_of(id2) & 31][c_new] = int16_t(id2);
-            }
-            cb = ca;
-          }
-          lane_col[l][cb] = int16_t(id);
-          bank_col[bnk][cb] = int16_t(id);
+          if (pick < 0) { pending[np++] = r; continue; }
+          used_e[r - r0][pick] = 1;
+          bank_used |= 1u << (row_ent[size_t(r) * kRowCap + pick] & 31);
+          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
+        }
+        for (int q = 0; q < np; ++q) {
+          const int r = pending[q];
+          int pick = -1;
+          for (int e = 0; e < row_n[r] && pick < 0; ++e) if (!used_e[r - r0][e]) pick = e;
+          used_e[r - r0][pick] = 1;
+          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
         }
       }
-      for (int l = 0; l < r1 - r0; ++l)
-        for (int c = 0; c < C; ++c)
-          if (lane_col[l][c] >= 0) put(l, c, ent_of(lane_col[l][c]));
     }
     // scratch slot of each row: vertex's slots are ordered by (tile, chunk)
     for (int i = 0; i < nv; ++i) {

@@ -29,7 +29,7 @@ static_assert(sizeof(TileHeader) == 64, "TileHeader must be 64 bytes");
 // vertex with in-tile degree d owns ceil(d / kRowCap) rows, each with its own scratch slot.
 constexpr int kRowCap = 16;
 inline int rows_cap(int tt, int nv) { return nv + 8 * tt / kRowCap; }           // rows per tile upper bound
-inline int ell_cap(int tt, int nv) { return 12 * tt + 32 * kRowCap + rows_cap(tt, nv) + 64; }  // entries the kernel stages in smem
+inline int ell_cap(int tt, int nv) { return 8 * tt + 32 * kRowCap + rows_cap(tt, nv) + 64; }  // entries upper bound
 // Vertex blob of one tile (NV = max_local_vertices, NR = rows_cap):
 //   TileHeader | vlist int[NV] | X float[NV] | YZ float2[NV] | slot int[NR] | grp_ptr int[NR/32 + 4]
 // `slot` (row order) is where the row's partial gradient goes in the float4 scratch array; the
@@ -61,7 +61,6 @@ struct PlanOptions {
   int32_t max_local_vertices = 384; // capacity NV of the compiled kernel variant
   int32_t laplacian_scale = 0;
   int32_t balance_sms = 148;        // >0: pick the tile fill so the tile count is a multiple of this
-  int32_t colour_rows = 1;          // conflict-free (edge-coloured) gather rows; 0 = dense rows, greedy order
 };
 
 // Returns 0 on success, TSB_E_* otherwise (message in err).
