@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define TSB_VERSION 1
+#define TSB_VERSION 2
 
 enum {
   TSB_OK = 0,
@@ -33,32 +33,39 @@ enum {
 typedef struct tsb_handle_s *tsb_handle_t;
 
 typedef struct {
-  int32_t tile_tets;        /* tets per tile (CTA work unit); 0 = library default               */
+  int32_t warps_per_cta;    /* 0 = library default (16, one persistent CTA per SM); 8 = two CTAs per SM */
   int32_t laplacian_scale;  /* 0 = unscaled tet-graph Laplacian (what the reference requests:
                                tet_spheres.cpp:148 passes (1, 0)); 1 = rows divided by #nbrs    */
-  int32_t reserved[6];
+  int32_t ring_slots;       /* per-warp TMA ring depth in chunks of 6 cells: 0 = default (2); 2..8   */
+  int32_t force_global;     /* 1: gather u/x from global memory instead of staging components in
+                               shared memory (the mode used for components too large to stage)   */
+  int32_t tet_cost_x100;    /* load-balance weight of one tet vs one operator entry, x100 (0 = default) */
+  int32_t reserved[3];
 } tsb_options_t;
 
 typedef struct {
   int32_t n;                /* vertices                                                          */
   int32_t nele;             /* tets                                                              */
-  int32_t n_tiles;          /* CTAs per launch                                                   */
-  int32_t tile_tets;
   int32_t n_components;     /* connected components (= tet-spheres)                              */
-  int32_t n_shared_vertices;/* vertices touched by more than one tile                            */
-  int64_t n_local_vertices; /* sum over tiles of staged vertices (duplication = this / n)        */
-  int64_t device_bytes;     /* bytes of device memory owned by the handle                        */
-  int64_t stream_bytes;     /* bytes one launch reads+writes from the handle's arrays + x + grad */
+  int32_t grid;             /* persistent CTAs per launch                                        */
+  int32_t warps_per_cta;
+  int32_t ctas_per_sm;
+  int32_t mode_global;      /* 0 = components staged in shared memory, 1 = global gathers        */
+  int32_t smem_bytes;       /* dynamic shared memory per CTA                                     */
+  int32_t ring_slots;
+  int32_t n_segments;       /* (CTA, component) work pieces                                      */
   int32_t n_boundary_faces;
-  int32_t max_local_vertices;
-  int32_t fill;             /* tets per tile actually used (<= tile_tets; wave-balanced)         */
-  int32_t reserved;
+  int32_t max_component_vertices;
+  int64_t nnz;              /* off-diagonal entries of M = G^T L^T L G (per coordinate)          */
+  int64_t nnz_padded;       /* entries stored in the row blocks (incl. padding)                  */
+  int64_t device_bytes;     /* bytes of device memory owned by the handle                        */
+  int64_t stream_bytes;     /* bytes one launch reads+writes: plan streams + rest + x + grad     */
 } tsb_info_t;
 
 /* Replaces TetSpheres::TetSpheres(int nv, double*, int ntet, int*) + TetSpheres::init
  * (tssplat_ext/tet_spheres/tet_spheres.cpp:119-126,140-203) and the libpgo operator builders it
- * calls (:148-149): builds per-tet rest inverses, face adjacency and the tile plan on the host,
- * uploads them to `device`.  rest_xyz: host float32 [3n] REST positions; tets: host int32
+ * calls (:148-149): builds the rows of M = G^T L^T L G (fp64, rounded to fp32 like :43-45), the
+ * per-tet 1/det(Dm), and the per-warp work streams on the host, and uploads them to `device`.  rest_xyz: host float32 [3n] REST positions; tets: host int32
  * [4*nele], 0-based.  opt may be NULL. */
 int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele,
                const tsb_options_t *opt, int device, tsb_handle_t *out);
@@ -74,21 +81,28 @@ int tsb_get_info(tsb_handle_t h, tsb_info_t *info);
 /* THE HOT PATH.  Replaces tet_spheres_smooth_barrier + tet_spheres_smooth_barrier_backward
  * (tssplat_ext/tet_spheres/tet_spheres_cuda.cu:118-195 and :197-263: 5 cuSPARSE SpMVs, 2 kernels,
  * 3 cuBLAS calls and 3 host syncs) with ONE kernel launch and no host sync:
- *   energy_out[0] = c1 * 1/2 ||L G x||^2 + c2 * sum_t max(-det F_t,0)^order
- *   energy_out[1] = 1/2 ||L G x||^2          energy_out[2] = sum_t max(-det F_t,0)^order
+ *   energy_out[0] = c1 * 1/2 x^T G^T L^T L G x + c2 * sum_t max(-det F_t,0)^order
+ *   energy_out[1] = 1/2 x^T G^T L^T L G x    energy_out[2] = sum_t max(-det F_t,0)^order
  *   grad_out      = gradH * d energy_out[0] / d x          ([n,3] fp32, fully overwritten)
  * x_dev: device float32 [3n], contiguous.  gradH_dev: optional device float (0-dim tensor's
  * data pointer); when non-NULL it multiplies gradH (so pass gradH = 1).  grad_out_dev may be NULL
  * (energy only: replaces the forward alone).  order must be 2 or 4 (the reference silently
- * returns zeros otherwise: cu:57-63). */
+ * returns zeros otherwise: cu:57-63).  One launch may be in flight per handle at a time (the handle
+ * owns counters and scratch, like the reference's TetSpheres: tet_spheres.h:37); launches on one
+ * stream are chained with programmatic dependent launch.  Results are bitwise repeatable when no tet
+ * is inverted; inverted tets add their barrier gradient with red.global.add.f32 (order-dependent
+ * rounding in the affected vertices only). */
 int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order,
                     float gradH, const float *gradH_dev, float *energy_out_dev,
                     float *grad_out_dev, void *stream);
 
 /* Same computation for callers whose vertex positions live in HOST memory (e.g. a CPU-side
- * optimiser): copies x_host -> device, runs the fused launch, copies energy[3] and grad back, all
- * asynchronously on `stream`; the host buffers must stay valid until the stream has been
- * synchronised (pinned memory makes the copies truly asynchronous).  grad_out_host may be NULL.
+ * optimiser): copies x_host -> device, runs the fused launch, copies energy[3] and grad back,
+ * asynchronously; the outputs are valid once `stream` has been synchronised and the host buffers
+ * must stay valid until then (pinned memory makes the copies truly asynchronous).  x_host must be
+ * fully written by the CPU when the call is made: its upload runs on an internal copy stream so
+ * that it overlaps the previous call's kernel and download (double-buffered staging), i.e. it is
+ * NOT ordered after earlier work queued on `stream`.  grad_out_host may be NULL.
  * Replaces the reference's implicit host round trips (the CPU scalar at tet_spheres_cuda.cu:194 and
  * the caller's .cpu() of the gradient). */
 int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2, int32_t order,
@@ -102,7 +116,9 @@ int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH
 /* Replaces tet_spheres_grad_limit (tet_spheres_cuda.cu:265-303) with what it was meant to do
  * (the reference reads grad[0] instead of the arg-max element and is unused by the trainer):
  * if max|grad| > s_threshold, grad *= s / max|grad|.  No host sync. */
-int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, void *stream);
+/* work_dev: device float32 [4] scratch owned by the caller (zero-initialised once; the kernels leave
+ * it zeroed), one per concurrently used stream -- like tsb_adam_uniform_step. */
+int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, float *work_dev, void *stream);
 
 /* "Next" row (f)1: AdamUniform.step (utils/optimizer.py:37-89) as two launches and no sync.
  * p, g1, g2: device float32 [count]; step is the 1-based step number AFTER increment.  lr and the

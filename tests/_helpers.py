@@ -44,167 +44,175 @@ class COracle:
         return float(c1) * terms[0] + float(c2) * terms[1], terms, g
 
 
-_ARRAYS = {"vblob": np.uint8, "tblob": np.uint8, "ell": np.uint16, "slot_ptr": np.int32,
-           "tet_order": np.int32, "tile_first": np.int32}
-_HDR = ("ntet", "nvert", "nrow", "ell_off", "nell")
-ROW_CAP = 16
+PLAN_DEBUG_SO = os.path.join(ROOT, "tests", "native", "libtsb_plan_debug.so")
+_ARRAYS = {"stream": np.uint8, "X4": np.float32, "vlist": np.int32, "segs": np.int32, "cta_seg": np.int32,
+           "wdesc": np.uint32, "wseg": np.uint16, "orphans": np.int32, "pos16": np.uint16, "pos_gid": np.int32}
+_SCALARS = ("n", "nele", "n_components", "n_boundary_faces", "laplacian_scale", "mode_global", "nw", "grid", "vh",
+            "area_verts", "max_comp_verts", "contiguous", "nnz", "nnz_padded", "n_rb", "n_tetcells",
+            "gather_wf", "gather_wf_ideal", "tet_wf", "tet_wf_ideal")
+_SEG = ("comp", "vbase", "nv", "x4off", "expected", "whole", "npos", "p4off")
 
 
-def rows_cap(tt, nv):
-    return nv + 8 * tt // ROW_CAP
-
-
-def vblob_bytes(tt, nv):
-    nr = rows_cap(tt, nv)
-    return 64 + 16 * nv + 4 * nr + 4 * (nr // 32 + 4)
-
-
-def build_host_plan(rest, tets, tile_tets=512, laplacian_scale=0, balance_sms=0):
-    """Run the product's host plan builder (no CUDA) and copy its arrays out as numpy."""
-    from tssplat_b200 import _capi
-    lib = _capi.lib
-    lib.tsb_debug_plan_build.restype = C.c_int
-    lib.tsb_debug_plan_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                         C.c_int32, C.POINTER(C.c_void_p)]
-    lib.tsb_debug_plan_array.restype = C.c_int
-    lib.tsb_debug_plan_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
-                                         C.POINTER(C.c_int32)]
-    lib.tsb_debug_plan_scalars.argtypes = [C.c_void_p, C.c_void_p]
-    lib.tsb_debug_plan_free.argtypes = [C.c_void_p]
+def build_host_plan(rest, tets, nw=16, grid=148, laplacian_scale=0, force_global=0, vh_cap=0, area_cap=0,
+                    tet_cost=0.0):
+    """Run the product's host plan builder (tssplat_b200/csrc/tsb_plan.cpp, no CUDA) through the
+    test-only inspection library and copy its arrays out as numpy."""
+    lib = C.CDLL(PLAN_DEBUG_SO)
+    lib.tsbdbg_build.restype = C.c_int
+    lib.tsbdbg_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_void_p)]
+    lib.tsbdbg_array.restype = C.c_int
+    lib.tsbdbg_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int32)]
+    lib.tsbdbg_scalars.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tsbdbg_free.argtypes = [C.c_void_p]
+    lib.tsbdbg_last_error.restype = C.c_char_p
     rest = np.ascontiguousarray(np.asarray(rest, dtype=np.float32).reshape(-1))
     tets = np.ascontiguousarray(np.asarray(tets, dtype=np.int32).reshape(-1))
     d = C.c_void_p()
-    rc = lib.tsb_debug_plan_build(rest.ctypes.data, tets.ctypes.data, rest.size // 3, tets.size // 4,
-                                  int(tile_tets), int(laplacian_scale), int(balance_sms), C.byref(d))
+    rc = lib.tsbdbg_build(rest.ctypes.data, tets.ctypes.data, rest.size // 3, tets.size // 4, int(nw), int(grid),
+                          int(laplacian_scale), int(force_global), int(vh_cap), int(area_cap), float(tet_cost),
+                          C.byref(d))
     if rc != 0:
-        raise RuntimeError(_capi.last_error(None))
+        raise RuntimeError(lib.tsbdbg_last_error().decode())
     try:
         plan = {}
         for name, dt in _ARRAYS.items():
             ptr, cnt, eb = C.c_void_p(), C.c_int64(), C.c_int32()
-            assert lib.tsb_debug_plan_array(d, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(eb)) == 0, name
+            assert lib.tsbdbg_array(d, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(eb)) == 0, name
             nbytes = cnt.value * eb.value
             buf = (C.c_char * nbytes).from_address(ptr.value) if nbytes else b""
             plan[name] = np.frombuffer(bytes(buf), dtype=dt).copy()
-        sc = np.zeros(10, np.int32)
-        lib.tsb_debug_plan_scalars(d, sc.ctypes.data)
-        for k, v in zip(("n", "nele", "tile_tets", "max_local_vertices", "n_tiles", "n_components",
-                         "n_shared_vertices", "n_slots", "fill", "ell_cap"), sc):
+        sc = np.zeros(20, np.int64)
+        lib.tsbdbg_scalars(d, sc.ctypes.data)
+        for k, v in zip(_SCALARS, sc):
             plan[k] = int(v)
-        plan["laplacian_scale"] = int(laplacian_scale)
     finally:
-        lib.tsb_debug_plan_free(d)
-    # unpack the per-tile blobs
-    TT, NV = plan["tile_tets"], plan["max_local_vertices"]
-    VB, TB, NR = vblob_bytes(TT, NV), 52 * TT, rows_cap(TT, NV)
-    tiles = []
-    for t in range(plan["n_tiles"]):
-        vb = plan["vblob"][t * VB:(t + 1) * VB]
-        tb = plan["tblob"][t * TB:(t + 1) * TB]
-        hdr = dict(zip(_HDR, vb[:20].view(np.int32)))
-        nv, nt = int(hdr["nvert"]), int(hdr["ntet"])
-        tiles.append(dict(
-            hdr, vlist=vb[64:64 + 4 * NV].view(np.int32)[:nv],
-            X=np.stack([vb[64 + 4 * NV:64 + 8 * NV].view(np.float32)[:nv],
-                        vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 0],
-                        vb[64 + 8 * NV:64 + 16 * NV].view(np.float32).reshape(-1, 2)[:nv, 1]], axis=1),
-            slot=vb[64 + 16 * NV:64 + 16 * NV + 4 * NR].view(np.int32)[:int(hdr["nrow"])],
-            grp_ptr=vb[64 + 16 * NV + 4 * NR:].view(np.int32)[:(int(hdr["nrow"]) + 31) // 32 + 1],
-            idx8=tb[:16 * TT].view(np.uint16).reshape(-1, 8)[:nt],
-            B=tb[16 * TT:].view(np.float32).reshape(-1, 9)[:nt]))
-    plan["tiles"] = tiles
+        lib.tsbdbg_free(d)
+    plan["segs"] = [dict(zip(_SEG, row)) for row in plan["segs"].reshape(-1, 8).tolist()]
     return plan
 
 
 def emulate_kernel(plan, x, c1, c2, order, gradH=1.0, dtype=np.float64):
-    """numpy re-enactment of tsb_kernels.cu (tile kernel phases 0-2 + combine kernel) on the host
-    plan: same formulas, same data structures, tile by tile.
-    Returns (energy_total, smooth, barrier, grad[n,3])."""
-    TT = plan["tile_tets"]
-    TTP = TT + 4
-    x = np.asarray(x, dtype=np.float32).reshape(-1, 3).astype(dtype)
+    """numpy re-enactment of energy_grad_kernel (tsb_kernels.cu) on the host plan: every CTA, every
+    warp walks its cell stream exactly as the kernel does (row blocks, then tet cells, segment by
+    segment), with the same formulas.  Returns (energy_total, smooth, barrier, grad[n,3])."""
+    G, NW, glob = plan["grid"], plan["nw"], bool(plan["mode_global"])
+    IB = 4 if glob else 2
+    idt = np.uint32 if glob else np.uint16
+    CELL = 1024 if glob else 768
+    TPL = 1 if glob else 2
+    st = plan["stream"]
+    x = np.asarray(x, dtype=np.float32).reshape(-1, 3)
     n = plan["n"]
-    scratch = np.full((max(plan["n_slots"], 1), 3), np.nan, dtype=dtype)
-    es_tot = eb_tot = 0.0
-    for ti, td in enumerate(plan["tiles"]):
-        nt, nv = int(td["ntet"]), int(td["nvert"])
-        vl = td["vlist"]
-        xs = x[vl]                                              # phase 0
-        Xs = td["X"].astype(dtype)
-        ids = td["idx8"].astype(np.int64)
-        own, oppr = ids[:, :4], ids[:, 4:]
-        valid = (oppr & 0x8000) != 0
-        opp = oppr & 0x7FFF
-        assert own.max() < nv and opp.max() < nv
-        assert np.all(opp[~valid] == own[~valid]), "boundary faces must point at the own vertex"
-        B = td["B"].reshape(nt, 3, 3).astype(dtype)             # rows a1..a3
-        a = np.concatenate([-B.sum(axis=1, keepdims=True), B], axis=1)              # nt x 4 x 3
-        p = xs[own]                                             # nt x 4 x 3
-        e = p[:, 1:, :] - p[:, :1, :]                           # e[j][r]
-        F = np.einsum("tjr,tjc->trc", e, a[:, 1:, :])
-        J = np.linalg.det(F)
-        inv = J < 0
-        m = np.where(inv, -J, 0.0)
-        if order == 2:
-            eb = m * m; coef = 2 * m
-        else:
-            eb = m ** 4; coef = 4 * m ** 3
-        cof = np.linalg.inv(np.where(np.abs(J)[:, None, None] > 0, F, np.eye(3)))
-        cof = np.transpose(cof, (0, 2, 1)) * J[:, None, None]   # cof(F) = det(F) F^-T
-        Pm = (-c2 * coef)[:, None, None] * cof
-        Pm[~inv] = 0
-        z = np.einsum("trc,tjc->tjr", Pm, a)                    # nt x 4 x 3
-        H = np.zeros((nt, 3, 3), dtype=dtype)
-        lam = np.zeros((nt, 4, 4), dtype=dtype)
-        rho = np.zeros((nt, 4), dtype=dtype)
-        deg = valid.sum(axis=1)
-        d_all = np.zeros((nt, 4, 3), dtype=dtype)
-        for k in range(4):
-            v = valid[:, k]
-            ok = opp[:, k]
-            r = Xs[ok] - Xs[own[:, 0]]
-            l123 = np.einsum("tjc,tc->tj", B, r)
-            l0 = 1 - l123.sum(axis=1)
-            lk = np.concatenate([l0[:, None], l123], axis=1)
-            lam[:, k, :] = np.where(v[:, None], lk, 0)
-            lkk = lk[:, k]
-            rho[:, k] = np.where(v, -1.0 / np.where(v, lkk, 1.0), 0.0)
-            d = (xs[ok] - p[:, 0, :]) - np.einsum("tj,tjr->tr", l123, e)
-            d_all[:, k, :] = np.where(v[:, None], d, 0)
-            H += (rho[:, k, None] * d_all[:, k, :])[:, :, None] * a[:, k, None, :]
-        w = np.where(plan["laplacian_scale"] & (deg > 0), 1.0 / np.maximum(deg, 1), 1.0)
-        H *= w[:, None, None]
-        es = 0.5 * (H * H).sum(axis=(1, 2))
-        y = (c1 * w)[:, None, None] * rho[:, :, None] * np.einsum("trc,tkc->tkr", H, a)   # nt x 4 x 3
-        y = np.where(valid[:, :, None], y, 0)
-        z = z - np.einsum("tkj,tkr->tjr", lam, y)
-        outb = np.full((24, TTP), np.nan, dtype=dtype)          # phase 1 table
-        outb[0:3, TT] = 0.0                                     # zero column
-        for j in range(4):
-            for r in range(3):
-                outb[j * 3 + r, :nt] = z[:, j, r]
-                outb[(4 + j) * 3 + r, :nt] = y[:, j, r]
-        es_tot += es.sum(); eb_tot += eb.sum()
-        # phase 2: sliced-ELL gather (entries are word offsets into the [24][TT+4] table, stored as
-        # [k/2][lane][2] pairs; padding points at the zero column)
-        gp = td["grp_ptr"]
-        nrow = int(td["nrow"])
-        ngrp = (nrow + 31) // 32
-        flat = outb.reshape(-1)
-        ell = plan["ell"][td["ell_off"]: td["ell_off"] + td["nell"]]
-        n_real = 0
-        for r in range(nrow):
-            g, lane = r >> 5, r & 31
-            blk = ell[gp[g]: gp[g + 1]].reshape(-1, 32, 2).astype(np.int64)
-            assert blk.shape[0] * 2 <= ROW_CAP
-            ent = blk[:, lane, :].reshape(-1)
-            n_real += int((ent != TT).sum())
-            sl = int(td["slot"][r])
-            assert np.isnan(scratch[sl, 0]), "scratch slot written twice"
-            scratch[sl] = [flat[ent + c * TTP].sum() for c in range(3)]
-        assert n_real == int(4 * nt + valid.sum()), "gather table must list every (tet, slot) exactly once"
-    # combine kernel
-    sp = plan["slot_ptr"]
-    assert sp[0] == 0 and sp[-1] == plan["n_slots"] and not np.isnan(scratch[:plan["n_slots"]]).any()
-    grad = np.stack([gradH * scratch[sp[v]:sp[v + 1]].sum(axis=0) for v in range(n)])
-    return c1 * es_tot + c2 * eb_tot, es_tot, eb_tot, grad
+    grad = np.full((n, 3), np.nan, dtype=dtype)
+    grad[plan["orphans"]] = 0.0
+    bar_add = np.zeros((n, 3), dtype=dtype)
+    es = eb = 0.0
+    X4 = plan["X4"].reshape(-1, 4)
+    wdesc = plan["wdesc"].reshape(G, NW, 2)
+    wseg = plan["wseg"].reshape(-1, NW, 2)
+    cta_seg = plan["cta_seg"].reshape(G, 2)
+    rows_done = np.zeros(plan["n_components"], dtype=np.int64)
+    rows_seen = 0
+    lanes = np.arange(32)
+    for b in range(G):
+        pos = [int(wdesc[b, w, 0]) * 16 for w in range(NW)]
+        end = [pos[w] + int(wdesc[b, w, 1]) for w in range(NW)]
+        assert all(int(wdesc[b, w, 1]) % CELL == 0 for w in range(NW))
+        for s in range(cta_seg[b, 0], cta_seg[b, 1]):
+            h = plan["segs"][s]
+            nv = h["nv"]
+            if glob:
+                gids = np.arange(n)
+                U = (x - X4[:, :3]).astype(dtype)                       # float32 subtraction, like the kernel
+                Pp = x.astype(dtype)
+                to_local = lambda a, base=None: a.astype(np.int64)
+            else:
+                vg = (h["vbase"] + np.arange(nv)) if h["vbase"] >= 0 else plan["vlist"][h["x4off"]:h["x4off"] + nv]
+                npos = h["npos"]
+                spos = plan["pos16"][h["x4off"]:h["x4off"] + nv].astype(np.int64)
+                assert len(set(spos.tolist())) == nv and spos.max() < npos, "staging positions must be distinct"
+                gids = plan["pos_gid"][h["p4off"]:h["p4off"] + npos].astype(np.int64)      # position -> global id
+                assert np.array_equal(gids[spos], vg)
+                U = np.full((npos, 3), np.nan, dtype=dtype)                                 # unused positions hold garbage
+                Pp = np.full((npos, 3), np.nan, dtype=dtype)
+                U[spos] = (x[vg] - X4[h["x4off"]:h["x4off"] + nv, :3]).astype(dtype)
+                Pp[spos] = x[vg].astype(dtype)
+                assert npos <= 2047 and npos <= plan["area_verts"] and (h["whole"] or npos <= plan["vh"])
+                nv = npos
+
+                li = s - cta_seg[b, 0]
+                ub = 0 if h["whole"] else (li & 1) * 2 * plan["vh"]
+                xb = h["npos"] if h["whole"] else ub + plan["vh"]
+
+                def to_local(a, base=None):
+                    a = a.astype(np.int64)
+                    assert np.all(a % 16 == 0)
+                    r = a // 16 - (ub if base is None else base)
+                    assert r.min() >= 0 and r.max() < nv
+                    return r
+            for w in range(NW):
+                nrb, ntc = (int(v) for v in wseg[s, w])
+                p = pos[w]
+                for _ in range(nrb):
+                    acc = np.zeros((32, 3), dtype=dtype)
+                    e = np.zeros(32, dtype=dtype)
+                    q, len4 = 0, 1
+                    while q < len4:
+                        idx = to_local(st[p:p + 128 * IB].view(idt).reshape(32, 4))
+                        wbits = st[p + 128 * IB:p + 128 * IB + 512].view(np.uint32).reshape(32, 4)
+                        wq = wbits.view(np.float32).astype(dtype)
+                        p += CELL
+                        if q == 0:
+                            hdr = wbits[:, 0]
+                            len4 = int((hdr[0] >> 24) & 63)
+                            llog = int(hdr[0] >> 30)
+                            rid = (hdr & 0xFFFFFF).astype(np.int64)
+                            active = rid != 0xFFFFFF
+                            assert np.all(((hdr >> 24) & 63) == len4) and np.all((hdr >> 30) == llog) and 1 <= len4 <= 62
+                            assert np.all(np.isfinite(wq[:, 0])), "header must read as a finite weight"
+                            r = idx[:, 0]
+                            ui = U[r]
+                        d = U[idx] - ui[:, None, :]
+                        assert np.all(d[:, 0 if q == 0 else slice(0, 0)] == 0)
+                        assert np.all(wq[~active][:, 1:] == 0)
+                        acc += np.einsum("lk,lkr->lr", wq, d)
+                        e += np.einsum("lk,lk->l", wq, (d * d).sum(axis=2))
+                        q += 1
+                    L = 1 << llog
+                    assert np.all(r.reshape(-1, L) == r.reshape(-1, L)[:, :1]), "the lanes of a row must be adjacent"
+                    tot = acc.reshape(-1, L, 3).sum(axis=1)            # shuffle reduction over the L lanes
+                    lead = (lanes % L == 0) & active
+                    ra = r[lead]
+                    assert np.array_equal(gids[ra], rid[lead]), "header row id must be the global id of the lane's row"
+                    assert np.isnan(grad[gids[ra]]).all(), "a vertex row has two writers"
+                    grad[gids[ra]] = gradH * c1 * tot[lead[::L]]
+                    uref = U[h["x4off"]] if glob else U[0]
+                    es += 0.5 * np.einsum("lr,lr->", ui[lead] - uref, tot[lead[::L]])
+                    rows_seen += int(lead.sum())
+                assert ntc == 0 or w < NW - 1 or NW == 1, "the signalling warp must own no tets"
+                for _ in range(ntc):
+                    idx = st[p:p + 128 * IB * TPL].view(idt).reshape(32 * TPL, 4)
+                    idx = to_local(idx) if glob else to_local(idx, xb)
+                    idet = st[p + 128 * IB * TPL:p + 128 * IB * TPL + 128 * TPL].view(np.float32).astype(dtype)
+                    p += CELL
+                    q = Pp[idx]
+                    e1, e2, e3 = q[:, 1] - q[:, 0], q[:, 2] - q[:, 0], q[:, 3] - q[:, 0]
+                    c23 = np.cross(e2, e3)
+                    J = np.einsum("lr,lr->l", e1, c23) * idet
+                    inv = J < 0
+                    m = np.where(inv, -J, 0.0)
+                    eb += (m ** order).sum()
+                    coef = order * m ** (order - 1)
+                    k = (-coef * idet * c2 * gradH)[:, None]
+                    g1, g2, g3 = k * c23, k * np.cross(e3, e1), k * np.cross(e1, e2)
+                    for g, col in ((-(g1 + g2 + g3), 0), (g1, 1), (g2, 2), (g3, 3)):
+                        np.add.at(bar_add, gids[idx[inv, col]], g[inv])
+                pos[w] = p
+            rows_done[h["comp"]] += 1
+        assert pos == end, "a warp did not consume exactly its stream"
+    for sg in plan["segs"]:
+        assert rows_done[sg["comp"]] == sg["expected"], "rows-done counter would never reach `expected`"
+    assert rows_seen == n - len(plan["orphans"]) and not np.isnan(grad).any()
+    return c1 * es + c2 * eb, es, eb, grad + bar_add

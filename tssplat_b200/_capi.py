@@ -10,7 +10,8 @@ import os
 
 from . import build as _build
 
-LIB_PATH = _build.LIB_PATH
+# TSSPLAT_B200_LIB: developer override (e.g. the -DTSB_TRACE profiling build of tools/trace_phases.py)
+LIB_PATH = os.environ.get("TSSPLAT_B200_LIB") or _build.LIB_PATH
 
 TSB_OK, TSB_E_INVALID, TSB_E_MESH, TSB_E_CUDA, TSB_E_NOMEM = 0, -1, -2, -3, -4
 
@@ -22,16 +23,17 @@ EXPORTED_SYMBOLS = (
 
 
 class tsb_options_t(C.Structure):
-    _fields_ = [("tile_tets", C.c_int32), ("laplacian_scale", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("warps_per_cta", C.c_int32), ("laplacian_scale", C.c_int32), ("ring_slots", C.c_int32),
+                ("force_global", C.c_int32), ("tet_cost_x100", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class tsb_info_t(C.Structure):
     _fields_ = [
-        ("n", C.c_int32), ("nele", C.c_int32), ("n_tiles", C.c_int32), ("tile_tets", C.c_int32),
-        ("n_components", C.c_int32), ("n_shared_vertices", C.c_int32),
-        ("n_local_vertices", C.c_int64), ("device_bytes", C.c_int64), ("stream_bytes", C.c_int64),
-        ("n_boundary_faces", C.c_int32), ("max_local_vertices", C.c_int32),
-        ("fill", C.c_int32), ("reserved", C.c_int32),
+        ("n", C.c_int32), ("nele", C.c_int32), ("n_components", C.c_int32), ("grid", C.c_int32),
+        ("warps_per_cta", C.c_int32), ("ctas_per_sm", C.c_int32), ("mode_global", C.c_int32),
+        ("smem_bytes", C.c_int32), ("ring_slots", C.c_int32), ("n_segments", C.c_int32),
+        ("n_boundary_faces", C.c_int32), ("max_component_vertices", C.c_int32),
+        ("nnz", C.c_int64), ("nnz_padded", C.c_int64), ("device_bytes", C.c_int64), ("stream_bytes", C.c_int64),
     ]
 
 
@@ -60,7 +62,7 @@ def _load() -> C.CDLL:
     lib.tsb_scale.restype = C.c_int
     lib.tsb_scale.argtypes = [vp, i64, f32, vp, vp, vp]
     lib.tsb_grad_limit.restype = C.c_int
-    lib.tsb_grad_limit.argtypes = [vp, i64, f32, f32, vp]
+    lib.tsb_grad_limit.argtypes = [vp, i64, f32, f32, vp, vp]
     lib.tsb_adam_uniform_step.restype = C.c_int
     lib.tsb_adam_uniform_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, i32, C.c_double, vp, vp]
     return lib

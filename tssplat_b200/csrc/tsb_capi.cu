@@ -4,8 +4,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -16,8 +14,12 @@
 struct tsb_handle_s {
   int device = 0;
   tsb::KParams kp{};
-  const int32_t *slot_ptr = nullptr;
-  float *stage_x = nullptr, *stage_grad = nullptr, *stage_energy = nullptr;   // tsb_energy_grad_host staging
+  tsb::LaunchConfig lc{};
+  // tsb_energy_grad_host: double-buffered upload staging on an internal copy stream
+  float *stage_x[2] = {nullptr, nullptr}, *stage_grad = nullptr, *stage_energy = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  unsigned host_calls = 0;
   tsb_info_t info{};
   std::vector<void *> allocs;
   std::string err;
@@ -26,8 +28,6 @@ struct tsb_handle_s {
 namespace {
 
 thread_local std::string g_create_err;
-std::mutex g_mu;
-std::map<int, float *> g_limit_work;  // per-device scratch for tsb_grad_limit
 
 struct DeviceGuard {
   int prev = -1;
@@ -39,21 +39,31 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// device that owns a device pointer (falls back to the current device)
+int device_of(const void *p) {
+  cudaPointerAttributes a{};
+  if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+  cudaGetLastError();
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
 int fail(tsb_handle_t h, int code, const std::string &msg) {
   if (h) h->err = msg; else g_create_err = msg;
   return code;
 }
 
 template <class T>
-int upload(tsb_handle_t h, const std::vector<T> &v, const T **out, size_t min_elems = 1) {
-  const size_t bytes = std::max(v.size(), min_elems) * sizeof(T);
+int upload(tsb_handle_t h, const T *src, size_t count, const T **out, size_t min_elems = 1) {
+  const size_t bytes = std::max(count, min_elems) * sizeof(T);
   void *d = nullptr;
   cudaError_t e = cudaMalloc(&d, bytes);
   if (e != cudaSuccess) return fail(h, TSB_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   h->allocs.push_back(d);
   h->info.device_bytes += int64_t(bytes);
-  if (!v.empty()) {
-    e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (count) {
+    e = cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
   }
   *out = static_cast<const T *>(d);
@@ -74,6 +84,13 @@ int alloc_zero(tsb_handle_t h, size_t elems, T **out) {
   return TSB_OK;
 }
 
+int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+
+struct Choice { int nw, ring, smem, ctas, global; };
+
 }  // namespace
 
 extern "C" {
@@ -82,66 +99,128 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
                int device, tsb_handle_t *out) {
   if (!out) return fail(nullptr, TSB_E_INVALID, "out is null");
   *out = nullptr;
-  tsb::PlanOptions po;
+  tsb::PlanConfig pc;
+  int nw = env_int("TSSPLAT_B200_WARPS", 16), ring = env_int("TSSPLAT_B200_RING_SLOTS", 2);
+  const int cpc = std::max(1, std::min(8, env_int("TSSPLAT_B200_CELLS_PER_CHUNK", 6)));
+  int tet_cost_x100 = env_int("TSSPLAT_B200_TET_COST_X100", 0);
   if (opt) {
-    if (opt->tile_tets != 0) po.tile_tets = opt->tile_tets;
-    po.laplacian_scale = opt->laplacian_scale ? 1 : 0;
+    if (opt->warps_per_cta != 0) nw = opt->warps_per_cta;
+    if (opt->ring_slots != 0) ring = opt->ring_slots;
+    if (opt->tet_cost_x100 > 0) tet_cost_x100 = opt->tet_cost_x100;
+    pc.laplacian_scale = opt->laplacian_scale ? 1 : 0;
+    pc.force_global = opt->force_global ? 1 : 0;
   }
-  if (const char *env = std::getenv("TSSPLAT_B200_TILE_TETS")) {
-    if (!(opt && opt->tile_tets != 0)) po.tile_tets = std::atoi(env);
-  }
-  po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
-  if (po.max_local_vertices == 0)
-    return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets " + std::to_string(po.tile_tets) + " (compiled: 256, 512, 1024)");
+  if (env_int("TSSPLAT_B200_FORCE_GLOBAL", 0)) pc.force_global = 1;
+  pc.max_lanes_per_row = std::max(1, std::min(4, env_int("TSSPLAT_B200_LANES_PER_ROW", pc.max_lanes_per_row)));
+  if (env_int("TSSPLAT_B200_TETCELL_COST_X100", 0) > 0) pc.tetcell_cost = float(env_int("TSSPLAT_B200_TETCELL_COST_X100", 0)) / 100.f;
+  if (nw != 8 && nw != 16) return fail(nullptr, TSB_E_INVALID, "warps_per_cta must be 8 or 16");
+  if (ring < 2 || ring > 8) return fail(nullptr, TSB_E_INVALID, "ring_slots must be in [2, 8]");
+  if (tet_cost_x100 > 0) pc.tet_cost = float(tet_cost_x100) / 100.f;
+  pc.nw = nw;
 
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(nullptr, TSB_E_CUDA, "no CUDA device " + std::to_string(device) + " (tssplat_b200 has no CPU path)");
+  }
   DeviceGuard guard(device);
   if (!guard.ok) return fail(nullptr, TSB_E_CUDA, "cannot select CUDA device " + std::to_string(device));
-  {
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) po.balance_sms = sms;
-    if (const char *env = std::getenv("TSSPLAT_B200_BALANCE")) po.balance_sms = std::atoi(env) ? po.balance_sms : 0;
-  }
+  int sms = 0, smem_optin = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0 ||
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess)
+    return fail(nullptr, TSB_E_CUDA, "cannot query the CUDA device");
+  pc.area_cap = std::min(tsb::kMaxStagedVerts, std::max(0, (smem_optin - tsb::energy_smem_bytes(nw, 2, cpc, 0, false) - 256) / 32));
+
+  // Called by the plan builder once the component sizes are known: pick the ring size that lets the
+  // staging area fit, query occupancy, return the persistent grid.
+  Choice ch{nw, ring, 0, 0, 0};
+  std::string cb_err;
+  pc.grid_cb = [&](int /*vh*/, int area_verts, bool &global_mode) -> int {
+    if (!global_mode) {
+      int r = ring;
+      while (r > 2 && tsb::energy_smem_bytes(nw, r, cpc, area_verts, false) > smem_optin) --r;
+      if (tsb::energy_smem_bytes(nw, r, cpc, area_verts, false) > smem_optin) global_mode = true;
+      else ch.ring = r;
+    }
+    ch.global = global_mode ? 1 : 0;
+    if (global_mode) while (ch.ring > 2 && tsb::energy_smem_bytes(nw, ch.ring, cpc, 0, true) > smem_optin) --ch.ring;
+    ch.smem = tsb::energy_smem_bytes(nw, ch.ring, cpc, global_mode ? 0 : area_verts, global_mode);
+    int ctas = 0;
+    cudaError_t e = tsb::energy_occupancy(nw, ch.smem, global_mode, &ctas);
+    if (e != cudaSuccess || ctas < 1) {
+      cb_err = std::string("kernel does not fit the device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "occupancy 0");
+      return 0;
+    }
+    const int want = env_int("TSSPLAT_B200_CTAS_PER_SM", nw == 16 ? 1 : 2);
+    ch.ctas = std::max(1, std::min(ctas, want));
+    return ch.ctas * sms;
+  };
 
   tsb::HostPlan plan;
   std::string err;
-  int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, plan, err);
-  if (rc != TSB_OK) return fail(nullptr, rc, err);
-
-  cudaError_t ce = tsb::prepare_energy_grad(po.tile_tets);
-  if (ce != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("kernel attribute setup: ") + cudaGetErrorString(ce));
+  int rc = tsb::build_plan(rest_xyz, tets, n, nele, pc, plan, err);
+  if (rc != TSB_OK) return fail(nullptr, cb_err.empty() ? rc : TSB_E_CUDA, cb_err.empty() ? err : cb_err);
 
   tsb_handle_t h = new tsb_handle_s();
   h->device = device;
   tsb::KParams &kp = h->kp;
 #define TSB_TRY(expr) do { rc = (expr); if (rc != TSB_OK) { g_create_err = h->err; tsb_destroy(h); return rc; } } while (0)
-  TSB_TRY(upload(h, plan.vblob, &kp.vblob, 16));
-  TSB_TRY(upload(h, plan.tblob, &kp.tblob, 16));
-  TSB_TRY(upload(h, plan.ell, &kp.ell, 8));
-  TSB_TRY(upload(h, plan.slot_ptr, &h->slot_ptr, 2));
+  TSB_TRY(upload(h, plan.stream.data(), plan.stream.size(), &kp.stream, 16));
   {
-    const int32_t *te = nullptr;
-    TSB_TRY(upload(h, plan.tile_ell, &te, 2));
-    kp.tile_ell = reinterpret_cast<const int2 *>(te);
+    const float *x4 = nullptr;
+    TSB_TRY(upload(h, plan.X4.data(), plan.X4.size(), &x4, 4));
+    kp.X4 = reinterpret_cast<const float4 *>(x4);
+    const tsb::SegHdr *sg = nullptr;
+    TSB_TRY(upload(h, plan.segs.data(), plan.segs.size(), &sg, 1));
+    kp.segs = sg;
+    const int32_t *cs = nullptr;
+    TSB_TRY(upload(h, plan.cta_seg.data(), plan.cta_seg.size(), &cs, 2));
+    kp.cta_seg = reinterpret_cast<const int2 *>(cs);
+    const uint32_t *wd = nullptr;
+    TSB_TRY(upload(h, plan.wdesc.data(), plan.wdesc.size(), &wd, 2));
+    kp.wdesc = reinterpret_cast<const uint2 *>(wd);
+    const uint16_t *wsg = nullptr;
+    TSB_TRY(upload(h, plan.wseg.data(), plan.wseg.size(), &wsg, 2));
+    kp.wseg = reinterpret_cast<const ushort2 *>(wsg);
   }
-  TSB_TRY(alloc_zero(h, size_t(plan.n_slots) * 4, &kp.scratch));
-  TSB_TRY(alloc_zero(h, size_t(plan.n_tiles) * 2, &kp.tile_energy));
+  TSB_TRY(upload(h, plan.vlist.data(), plan.vlist.size(), &kp.vlist, 1));
+  TSB_TRY(upload(h, plan.pos16.data(), plan.pos16.size(), &kp.pos16, 2));
+  TSB_TRY(upload(h, plan.pos_gid.data(), plan.pos_gid.size(), &kp.pos_gid, 1));
+  TSB_TRY(upload(h, plan.orphans.data(), plan.orphans.size(), &kp.orphans, 1));
+  TSB_TRY(alloc_zero(h, size_t(plan.n_components), &kp.done));
+  {
+    std::vector<unsigned long long> init(size_t(plan.grid) * 2, tsb::kEnergySentinel);
+    const unsigned long long *ce = nullptr;
+    TSB_TRY(upload(h, init.data(), init.size(), &ce, 2));
+    kp.cta_energy = reinterpret_cast<double *>(const_cast<unsigned long long *>(ce));
+  }
+#ifdef TSB_TRACE
+  TSB_TRY(alloc_zero(h, size_t(plan.grid) * 16, &kp.trace));
+#endif
+  if (plan.mode_global) {
+    TSB_TRY(alloc_zero(h, size_t(plan.n), &kp.u4g));
+    TSB_TRY(alloc_zero(h, size_t(plan.n), &kp.x4g));
+  }
 #undef TSB_TRY
-  kp.laplacian_scale = plan.laplacian_scale;
-  kp.n_tiles = plan.n_tiles;
-  kp.fill = plan.fill;
+  kp.n_orphans = int32_t(plan.orphans.size());
+  kp.n_components = plan.n_components;
+  kp.n = plan.n;
+  kp.vh = plan.vh;
+  kp.ring_bytes = tsb::energy_ring_bytes(ch.ring, cpc, plan.mode_global != 0);
+  kp.cells_per_chunk = cpc;
+  kp.stage_bytes = plan.mode_global ? 0 : plan.area_verts * 32;
+  h->lc = tsb::LaunchConfig{nw, plan.grid, ch.smem, plan.mode_global};
 
   tsb_info_t &I = h->info;
-  I.n = plan.n; I.nele = plan.nele; I.n_tiles = plan.n_tiles; I.tile_tets = plan.tile_tets;
-  I.n_components = plan.n_components; I.n_shared_vertices = plan.n_shared_vertices;
-  I.n_local_vertices = plan.n_local_vertices; I.n_boundary_faces = plan.n_boundary_faces;
-  I.max_local_vertices = plan.max_local_vertices;
-  I.fill = plan.fill;
-  // bytes one launch requests from the memory system: the fixed-size vertex-blob and tet-blob TMA
-  // copies, the gather tables, x gathered per staged vertex (12 B), grad (12 B/vertex), the
-  // shared-vertex partials written + read back, per-tile energies
-  I.stream_bytes = int64_t(plan.n_tiles) * (tsb::vblob_bytes(plan.tile_tets, plan.max_local_vertices) + int64_t(52) * plan.fill) +
-                   int64_t(plan.ell.size()) * 2 + plan.n_local_vertices * 12 + int64_t(plan.n) * (12 + 4) +
-                   int64_t(plan.n_slots) * 32 + int64_t(plan.n_tiles) * 16;
+  I.n = plan.n; I.nele = plan.nele; I.n_components = plan.n_components; I.grid = plan.grid;
+  I.warps_per_cta = nw; I.ctas_per_sm = ch.ctas; I.mode_global = plan.mode_global; I.smem_bytes = ch.smem;
+  I.ring_slots = ch.ring; I.n_segments = int32_t(plan.segs.size()); I.n_boundary_faces = plan.n_boundary_faces;
+  I.max_component_vertices = plan.max_comp_verts; I.nnz = plan.nnz; I.nnz_padded = plan.nnz_padded;
+  // bytes one launch requests: the warp streams, rest positions + x per staged component copy, grad
+  int64_t staged = 0;
+  for (const tsb::SegHdr &s : plan.segs) staged += s.nv;
+  I.stream_bytes = int64_t(plan.stream.size()) + (plan.mode_global ? int64_t(plan.n) * (12 + 16 + 64) : staged * (16 + 12 + 2)) +
+                   int64_t(plan.n) * 12 + int64_t(plan.segs.size()) * 32 + int64_t(plan.grid) * (16 + 8 * nw);
   *out = h;
   return TSB_OK;
 }
@@ -149,6 +228,11 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
 void tsb_destroy(tsb_handle_t h) {
   if (!h) return;
   DeviceGuard guard(h->device);
+  for (int k = 0; k < 2; ++k) {
+    if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
+    if (h->ev_free[k]) cudaEventDestroy(h->ev_free[k]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void *p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -172,7 +256,7 @@ int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int3
   tsb::KParams kp = h->kp;
   kp.x = x_dev; kp.grad = grad_out_dev; kp.energy_out = energy_out_dev; kp.gradH_dev = gradH_dev;
   kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
-  cudaError_t e = tsb::launch_energy_grad(kp, h->info.tile_tets, h->info.n, h->slot_ptr, static_cast<cudaStream_t>(stream));
+  cudaError_t e = tsb::launch_energy_grad(kp, h->lc, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
@@ -181,22 +265,45 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
                          float *energy_out_host, float *grad_out_host, void *stream) {
   if (!h) return TSB_E_INVALID;
   if (!x_host || !energy_out_host) return fail(h, TSB_E_INVALID, "x_host and energy_out_host must be non-null");
+  if (order != 2 && order != 4) return fail(h, TSB_E_INVALID, "order must be 2 or 4");
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(h, TSB_E_CUDA, "cannot select the handle's CUDA device");
   const size_t nb = size_t(h->info.n) * 3 * sizeof(float);
-  if (!h->stage_x) {
-    int rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x);
+  if (!h->stage_x[0]) {
+    int rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x[0]);
+    if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x[1]);
     if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_grad);
     if (rc == TSB_OK) rc = alloc_zero(h, 4, &h->stage_energy);
     if (rc != TSB_OK) return rc;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_free[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("copy stream setup: ") + cudaGetErrorString(e));
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemcpyAsync(h->stage_x, x_host, nb, cudaMemcpyHostToDevice, st);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const int k = int(h->host_calls & 1u);
+  cudaError_t e;
+  if (cap == cudaStreamCaptureStatusNone) {
+    // upload on the copy stream as soon as the kernel that last read this staging buffer is done:
+    // overlaps the previous call's kernel + download
+    ++h->host_calls;
+    e = cudaStreamWaitEvent(h->copy_stream, h->ev_free[k], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, h->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_h2d[k], h->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_h2d[k], 0);
+  } else {
+    e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, st);   // inside a stream capture: keep it linear
+  }
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-  const int rc = tsb_energy_grad(h, h->stage_x, c1, c2, order, gradH, nullptr, h->stage_energy,
+  const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy,
                                  grad_out_host ? h->stage_grad : nullptr, stream);
   if (rc != TSB_OK) return rc;
-  e = cudaMemcpyAsync(energy_out_host, h->stage_energy, 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (cap == cudaStreamCaptureStatusNone) e = cudaEventRecord(h->ev_free[k], st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy, 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad, nb, cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
   return TSB_OK;
@@ -205,29 +312,17 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
 int tsb_scale(const float *g_dev, int64_t count, float gradH, const float *gradH_dev, float *out_dev, void *stream) {
   if (!g_dev || !out_dev || count < 0) return fail(nullptr, TSB_E_INVALID, "tsb_scale: null pointer or negative count");
   if (count == 0) return TSB_OK;
+  DeviceGuard guard(device_of(g_dev));
   cudaError_t e = tsb::launch_scale(g_dev, count, gradH, gradH_dev, out_dev, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("scale launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
 
-int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, void *stream) {
-  if (!grad_dev || count < 0) return fail(nullptr, TSB_E_INVALID, "tsb_grad_limit: null pointer or negative count");
+int tsb_grad_limit(float *grad_dev, int64_t count, float s_threshold, float s, float *work_dev, void *stream) {
+  if (!grad_dev || !work_dev || count < 0) return fail(nullptr, TSB_E_INVALID, "tsb_grad_limit: null pointer or negative count");
   if (count == 0) return TSB_OK;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, TSB_E_CUDA, "cudaGetDevice failed");
-  float *work = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_limit_work.find(dev);
-    if (it == g_limit_work.end()) {
-      if (cudaMalloc(reinterpret_cast<void **>(&work), 4 * sizeof(float)) != cudaSuccess || cudaMemset(work, 0, 4 * sizeof(float)) != cudaSuccess)
-        return fail(nullptr, TSB_E_NOMEM, "tsb_grad_limit: scratch allocation failed");
-      g_limit_work[dev] = work;
-    } else {
-      work = it->second;
-    }
-  }
-  cudaError_t e = tsb::launch_grad_limit(grad_dev, count, s_threshold, s, work, static_cast<cudaStream_t>(stream));
+  DeviceGuard guard(device_of(grad_dev));
+  cudaError_t e = tsb::launch_grad_limit(grad_dev, count, s_threshold, s, work_dev, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("grad_limit launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
@@ -237,61 +332,21 @@ int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, fl
   if (!p_dev || !grad_dev || !g1_dev || !g2_dev || !work_dev || count < 0 || step < 1)
     return fail(nullptr, TSB_E_INVALID, "tsb_adam_uniform_step: null pointer, negative count or step < 1");
   if (count == 0) return TSB_OK;
+  DeviceGuard guard(device_of(p_dev));
   cudaError_t e = tsb::launch_adam_uniform(p_dev, grad_dev, g1_dev, g2_dev, count, lr, beta1, beta2, step, grad_limit,
                                            work_dev, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(nullptr, TSB_E_CUDA, std::string("adam_uniform launch: ") + cudaGetErrorString(e));
   return TSB_OK;
 }
 
-/* ---- host-plan inspection (tests only; no CUDA calls): lets the CPU test-suite check the tile
- * plan -- staging lists, gather tables, shared-vertex combine lists -- without a GPU. ---------- */
-struct tsb_debug_plan_s { tsb::HostPlan plan; };
-
-int tsb_debug_plan_build(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t nele, int32_t tile_tets,
-                         int32_t laplacian_scale, int32_t balance_sms, tsb_debug_plan_s **out) {
-  if (!out) return TSB_E_INVALID;
-  *out = nullptr;
-  tsb::PlanOptions po;
-  if (tile_tets) po.tile_tets = tile_tets;
-  po.laplacian_scale = laplacian_scale;
-  po.max_local_vertices = tsb::nvmax_for(po.tile_tets);
-  if (po.max_local_vertices == 0) return fail(nullptr, TSB_E_INVALID, "unsupported tile_tets");
-  po.balance_sms = balance_sms;
-  tsb_debug_plan_s *d = new tsb_debug_plan_s();
-  std::string err;
-  const int rc = tsb::build_plan(rest_xyz, tets, n, nele, po, d->plan, err);
-  if (rc != TSB_OK) { delete d; return fail(nullptr, rc, err); }
-  *out = d;
-  return TSB_OK;
+#ifdef TSB_TRACE
+/* profiling build only: copy the [grid][16] phase stamps of the last launch to the host */
+int tsb_trace_read(tsb_handle_t h, unsigned long long *out, int64_t count) {
+  if (!h || !out) return TSB_E_INVALID;
+  DeviceGuard guard(h->device);
+  const int64_t have = int64_t(h->info.grid) * 16;
+  return cudaMemcpy(out, h->kp.trace, size_t(std::min(count, have)) * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? TSB_OK : TSB_E_CUDA;
 }
-
-/* name -> (pointer, element count, element bytes); returns TSB_E_INVALID for an unknown name */
-int tsb_debug_plan_array(tsb_debug_plan_s *d, const char *name, const void **ptr, int64_t *count, int32_t *elem_bytes) {
-  if (!d || !name || !ptr || !count || !elem_bytes) return TSB_E_INVALID;
-  const tsb::HostPlan &P = d->plan;
-  const std::string k(name);
-#define TSB_ARR(nm, vec) if (k == nm) { *ptr = (vec).data(); *count = int64_t((vec).size()); *elem_bytes = int32_t(sizeof((vec)[0])); return TSB_OK; }
-  TSB_ARR("vblob", P.vblob) TSB_ARR("tblob", P.tblob) TSB_ARR("ell", P.ell) TSB_ARR("slot_ptr", P.slot_ptr)
-  TSB_ARR("tet_order", P.tet_order) TSB_ARR("tile_first", P.tile_first) TSB_ARR("tile_ell", P.tile_ell)
-#undef TSB_ARR
-  return TSB_E_INVALID;
-}
-
-int tsb_debug_plan_scalars(tsb_debug_plan_s *d, int32_t *out8) {  /* out8: 10 ints */
-  if (!d || !out8) return TSB_E_INVALID;
-  const tsb::HostPlan &P = d->plan;
-  out8[0] = P.n; out8[1] = P.nele; out8[2] = P.tile_tets; out8[3] = P.max_local_vertices; out8[4] = P.n_tiles;
-  out8[5] = P.n_components; out8[6] = P.n_shared_vertices; out8[7] = P.n_slots; out8[8] = P.fill; out8[9] = tsb::ell_cap(P.tile_tets, P.max_local_vertices);
-  return TSB_OK;
-}
-
-void tsb_debug_plan_free(tsb_debug_plan_s *d) { delete d; }
-
-/* Tuning hook (not part of the stable ABI): threads per CTA for the 512-tet variant. */
-void tsb_debug_set_threads_512(int nt) { tsb::set_threads_512(nt); }
-void tsb_debug_set_skip_combine(int v) { tsb::set_skip_combine(v); }
-void tsb_debug_set_pdl_tile(int v) { tsb::set_pdl_tile(v); }
-void tsb_debug_set_exp_flags(int v) { tsb::set_exp_flags(v); }
-
+#endif
 
 }  // extern "C"

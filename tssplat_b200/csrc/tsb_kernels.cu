@@ -1,39 +1,29 @@
 // Fused geometry-energy + gradient kernel for sm_100a, plus the small level-1 helpers.
 //
-// One launch replaces the reference's forward+backward pipeline
+// ONE launch replaces the reference's forward+backward pipeline
 // (tssplat_ext/tet_spheres/tet_spheres_cuda.cu:118-263: SpMV GTLTLG.x, Sdot, SpMV G.x,
 // cuda_forward_det, Sasum, SpMV c1.GTLTLG.x, SpMV G.x again, cuda_backward_det, SpMV G^T, Sscal,
 // with three host syncs).
 //
-// Math.  For tet t with own vertices v0..v3, rest inverse B = Dm^-1 (rows
-// a1,a2,a3 are the rest gradients of the hat functions of v1..v3, a0 = -(a1+a2+a3)):
-//     F_t = sum_k x_vk (x) a_k                                (geometry/mesh_utils.py:38-69)
-// The reference's smoothness term 1/2 x^T G^T L^T L G x equals 1/2 sum_t ||H_t||^2 with
-// H_t = (L F)_t = deg_t F_t - sum_{s face-nbr t} F_s.  Two tets sharing a face agree on that face,
-// so F_s - F_t is rank one:  F_s - F_t = d_k (x) a_k / lambda_kk  where o_k is the vertex of s
-// opposite the shared face k, lambda_k. are the barycentric coordinates of REST(o_k) in t and
-//     d_k = x_ok - sum_j lambda_kj x_vj          (how far o_k is from t's affine map)
-// Hence  H_t = sum_k rho_k d_k (x) a_k,  rho_k = -1/lambda_kk > 0:  an 8-vertex stencil per tet
-// whose gradient scatters to those same 8 vertices -- no neighbour-tet intermediates, no 2-ring
-// passes, no grid sync.  The barrier term is the reference's: max(-det F,0)^p, p in {2,4}
-// (cu:48-66), gradient -p(-J)^(p-1) cof(F) (cu:68-102).
+// Math.  With u = x - X (X = rest positions):
+//   smoothness  1/2 x^T M x = 1/2 u^T M u        M = G^T L^T L G  (tet_spheres.cpp:148; M X = 0: affine maps are in its null space)
+//   M has zero row sums, so with d_ij = u_j - u_i
+//       (M u)_i        = sum_{j != i} M_ij d_ij
+//       1/2 u^T M u    = -1/4 sum_i sum_{j != i} M_ij |d_ij|^2
+//   which is what each lane evaluates for its vertex row: well conditioned near the rest state
+//   (the reference's fp32 x^T M x cancels there) and no scatter -- every gradient row has one writer.
+//   barrier     sum_t max(-J_t, 0)^p,  J_t = det F_t = det(Ds_t) / det(Dm_t)   (cu:48-66; F = Ds Dm^-1)
+//       dJ/dx_k = cof(Ds)[:,k] / det(Dm)  (k = 1..3),  dJ/dx_0 = -(sum)           (cu:68-102, :32-46)
+//   so a tet needs 4 vertex ids + one float; only inverted tets (rare) touch the gradient, with
+//   red.global.add.f32 after the component's rows have been stored (per-component counter).
 //
-// Execution.  Persistent CTAs (2 per SM, 256 threads) loop over tiles of <= TT tets / <= NV staged
-// vertices.  One thread issues TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of each tile's
-// vertex blob, tet blob and gather table from global to shared memory one tile ahead; the only
-// dependent global chain (vertex id -> x) is issued one phase ahead and lands in registers.
-//   phase 0  x (registers) + rest X (staged) -> float4 array in shared memory
-//   phase 1  one tet per thread, branch-free: 13 smem gathers, energy terms, 8 output 3-vectors
-//            written to a [24][TT+4] smem table (conflict-free stores)
-//   phase 2  one gather row per thread (<= 16 entries, bank-aware order, padding -> zero column):
-//            sum the table entries and store the partial gradient to the row's float4 scratch slot
-// A second, tiny kernel chained with programmatic dependent launch (griddepcontrol) sums each
-// vertex's slots in fixed order into grad (scaled by gradH) and folds the per-CTA energies in
-// fp64.  No atomics, no fences, no grid sync: bitwise deterministic.
-// History (profiles/r01_summary.md): a single-launch last-arriver combine cost 47% of warp time in
-// fences/atomics/barriers; a warp-specialised pipeline that overlapped the phases lost to shared-
-// memory contention (row gather 1.5k -> 4.3k cycles when it overlaps the tet math); overlapping
-// only the global-memory latency (this design) won.
+// Execution.  Persistent CTAs (1 per SM x 16 warps, or 2 x 8).  Every warp owns a private byte
+// stream of operator rows and tet blocks (tsb_plan.h) and pulls it through a private shared-memory
+// ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), issued by its lane 0, first
+// chunks before griddepcontrol.wait: plan data streams from HBM while the previous kernel drains.
+// Per segment the CTA stages u and x of the whole component in shared memory (float4 each; the next
+// component is prefetched through registers), so all gathers are LDS.128.  Energies: per-lane fp64
+// partials -> per-CTA pair -> last-arriving CTA folds them in fixed order (deterministic).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -45,11 +35,6 @@ namespace tsb {
 
 namespace {
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -79,361 +64,444 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  : "memory");
   } while (!ok);
 }
-
-constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
-int g_skip_combine = 0;   // developer switch (timing experiments only)
-int g_pdl_tile = 1;       // tile kernel launched with programmatic stream serialisation
-int g_exp_flags = 0;
-
-
-
-template <int TT, int NV>
-struct Smem {
-  static constexpr int NR = NV + 8 * TT / kRowCap;           // == rows_cap(TT, NV)
-  static constexpr int ELLCAP = 8 * TT + 32 * kRowCap + NR + 64;   // == ell_cap(TT, NV)
-  static constexpr int kVBytes = 64 + 16 * NV + 4 * NR + 4 * (NR / 32 + 4);
-  static constexpr int kVStage = align_up(kVBytes, 128);     // two vertex-blob stages
-  static constexpr int kTOff = 2 * kVStage;
-  static constexpr int kEllOff = align_up(kTOff + 52 * TT, 128);
-  static constexpr int kXs4Off = align_up(kEllOff + 2 * ELLCAP, 128);
-  static constexpr int kOutOff = align_up(kXs4Off + 16 * NV, 128);
-  static constexpr int kTTP = TT + 4;                 // output-table row stride; column TT holds zeros
-  static constexpr int kBytes = kOutOff + 96 * kTTP;
-};
-
-// Sum one vertex's table entries.  ep points at this lane's first (entry0, entry1) pair; pairs of
-// successive k are 32 words apart.  Padding entries point at the table's zero column.
-template <int TTP>
-__device__ __forceinline__ void gather_vertex(const float *outb, const uint32_t *ep, int len2, float &g0, float &g1, float &g2) {
-#pragma unroll 8
-  for (int k = 0; k < len2; ++k) {
-    const uint32_t pr = ep[k * 32];
-    const float *o0 = outb + (pr & 0xffffu), *o1 = outb + (pr >> 16);
-    g0 += o0[0]; g1 += o0[TTP]; g2 += o0[2 * TTP];
-    g0 += o1[0]; g1 += o1[TTP]; g2 += o1[2 * TTP];
-  }
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// One tet: 13 shared-memory gathers, barrier + smoothness energy terms, and (WITH_GRAD) its 8 output
-// 3-vectors written to column `lt` of the [24][TTP] table.  Shared by both tile kernels.
-template <int TTP, bool WITH_GRAD>
-__device__ __forceinline__ void tet_body(const int lt, const uint4 *__restrict__ idx_s, const float *__restrict__ B_s,
-                                         const float4 *__restrict__ xs4, const float2 *__restrict__ xs2,
-                                         float *__restrict__ outb, const float c1, const float c2, const int order,
-                                         const bool lscale, float &es, float &eb) {
-  const uint4 iv = idx_s[lt];
-  float b[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) b[i] = B_s[lt * 9 + i];
-  const unsigned iown[4] = {iv.x & 0xffffu, iv.x >> 16, iv.y & 0xffffu, iv.y >> 16};
-  const unsigned ioppr[4] = {iv.z & 0xffffu, iv.z >> 16, iv.w & 0xffffu, iv.w >> 16};
+constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
+constexpr int kMaxSlots = 8;
+constexpr unsigned long long kSentinel = kEnergySentinel;   // "no partial yet" marker in cta_energy (a NaN payload)
 
-  const float4 p0 = xs4[iown[0]];
-  const float2 q0 = xs2[iown[0]];
-  float e[3][3];  // e[j][r] = x_{v_{j+1}}[r] - x_{v0}[r]
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float4 pj = xs4[iown[j + 1]];
-    e[j][0] = pj.x - p0.x; e[j][1] = pj.y - p0.y; e[j][2] = pj.z - p0.z;
+// Profiling build only (-DTSB_TRACE, tools/trace_phases.py): thread 0 of every CTA stamps its phases.
+#ifdef TSB_TRACE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TSB_STAMP(i) do { if (tid == 0 && p.trace) p.trace[blockIdx.x * 16 + (i)] = (i) == 0 ? gtime() : (unsigned long long)clock64(); } while (0)
+#else
+#define TSB_STAMP(i) do { } while (0)
+#endif
+
+// shared-memory layout: staging area (offset 0: gather offsets in the plan are relative to it) | rings |
+// mbarriers | fp64 reduction scratch
+__host__ __device__ constexpr int off_rings(int stage_bytes) { return align_up(stage_bytes, 128); }
+__host__ __device__ constexpr int off_bars(int stage_bytes, int nw, int ring) { return off_rings(stage_bytes) + nw * ring; }
+__host__ __device__ constexpr int off_red(int stage_bytes, int nw, int ring) { return off_bars(stage_bytes, nw, ring) + nw * kMaxSlots * 8; }
+constexpr int kSegTab = 16;   // segment headers (and per-warp block counts) of a CTA cached in shared memory; beyond that: global
+__host__ __device__ constexpr int off_segtab(int stage_bytes, int nw, int ring) { return align_up(off_red(stage_bytes, nw, ring) + nw * 16, 32); }
+__host__ __device__ constexpr int off_wsegtab(int stage_bytes, int nw, int ring) { return off_segtab(stage_bytes, nw, ring) + kSegTab * 32; }
+__host__ __device__ constexpr int smem_total(int stage_bytes, int nw, int ring) { return align_up(off_wsegtab(stage_bytes, nw, ring) + kSegTab * nw * 4, 128); }
+
+// ---- packed fp32 pairs (Blackwell FFMA2) ----------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float sum2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a + b; }
+__device__ __forceinline__ void fma2_acc(f32x2 &acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
+template <bool GLOBAL> struct Fmt;
+template <> struct Fmt<false> { static constexpr uint32_t CELL = kCellStaged, IB = 2, TPL = 2; };   // 16-bit smem byte offsets
+template <> struct Fmt<true> { static constexpr uint32_t CELL = kCellGlobal, IB = 4, TPL = 1; };    // 32-bit vertex ids
+
+// Per-warp view of its TMA-fed cell stream: `cpc` cells per chunk, one chunk per ring slot, `nslot` slots.
+// Lane 0 keeps the producer state (next source address, bytes left to request).
+template <uint32_t CELL>
+struct WarpStream {
+  const unsigned char *next_src;   // lane 0: global address of the next chunk to request
+  uint32_t bytes_left;             // lane 0: bytes of the stream not yet requested
+  uint32_t bars;                   // shared-space address of this warp's mbarriers
+  unsigned char *ring;             // this warp's ring
+  unsigned char *cell;             // current cell
+  uint32_t chunk_bytes, cpc, nslot;
+  uint32_t cc, slot, phase, cells_left;
+  int lane;
+
+  __device__ __forceinline__ void request(uint32_t smem_dst, uint32_t bar) {   // lane 0 only
+    const uint32_t bytes = min(chunk_bytes, bytes_left);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(next_src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+    next_src += bytes;
+    bytes_left -= bytes;
   }
-  float4 po[4];
-  float2 qo[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { po[k] = xs4[ioppr[k] & 0x7fffu]; qo[k] = xs2[ioppr[k] & 0x7fffu]; }
-
-  // hat gradients: a[0] = -(a1+a2+a3), a[j] = row j-1 of B
-  float a[4][3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    a[1][c] = b[c]; a[2][c] = b[3 + c]; a[3][c] = b[6 + c];
-    a[0][c] = -(b[c] + b[3 + c] + b[6 + c]);
+  __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
   }
+  __device__ __forceinline__ void begin() {       // first chunk has landed
+    if (cells_left) wait(bars, 0);
+  }
+  // cells of the current chunk not yet consumed (the caller may read up to that many cells from `cell` on)
+  __device__ __forceinline__ uint32_t avail() const { return cpc - cc; }
+  // n <= avail() cells starting at `cell` have been read into registers
+  __device__ __forceinline__ void advance(uint32_t n) {
+    cell += n * CELL;
+    cc += n;
+    cells_left -= n;
+    if (cc == cpc) {                 // leave the chunk: refill its slot, wait for the next chunk
+      cc = 0;
+      __syncwarp();
+      if (lane == 0 && bytes_left) request(smem_u32(cell) - chunk_bytes, bars + slot * 8);
+      if (++slot == nslot) { slot = 0; cell = ring; phase ^= 1u; }
+      if (cells_left) wait(bars + slot * 8, phase);
+    }
+  }
+};
 
-  float z[3][3];  // gradient contributions to own vertices 1..3 (vertex 0 follows from momentum)
-#pragma unroll
-  for (int j = 0; j < 3; ++j) { z[j][0] = 0.f; z[j][1] = 0.f; z[j][2] = 0.f; }
+template <int NW, int MINB, bool GLOBAL>
+__global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParams p) {
+  using F = Fmt<GLOBAL>;
+  constexpr int NT = NW * 32;
+  constexpr uint32_t CELL = F::CELL, WOFF = 128 * F::IB;
+  constexpr int SV = GLOBAL ? 1 : (1024 + NT - 1) / NT;   // register-prefetch slots per thread (vh <= 1023)
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ring = p.ring_bytes, stage_bytes = p.stage_bytes;
+  TSB_STAMP(0); TSB_STAMP(1);
+  double *red = reinterpret_cast<double *>(smem + off_red(stage_bytes, NW, ring));
+  float4 *stage = reinterpret_cast<float4 *>(smem);
+
+  // ---- prologue: plan data only (overlaps the previous kernel under programmatic dependent launch)
+  const int2 cs = __ldg(&p.cta_seg[blockIdx.x]);
+  WarpStream<CELL> ws;
   {
-    float F[3][3];
+    const uint2 wd = __ldg(&p.wdesc[blockIdx.x * NW + warp]);
+    ws.next_src = p.stream + size_t(wd.x) * 16;
+    ws.bytes_left = wd.y;
+    ws.cells_left = wd.y / CELL;
+    ws.ring = smem + off_rings(stage_bytes) + warp * ring;
+    ws.bars = smem_u32(smem + off_bars(stage_bytes, NW, ring)) + warp * kMaxSlots * 8;
+    ws.cpc = uint32_t(p.cells_per_chunk);
+    ws.chunk_bytes = ws.cpc * CELL;
+    ws.nslot = uint32_t(ring) / ws.chunk_bytes;
+    ws.cell = ws.ring;
+    ws.cc = 0; ws.slot = 0; ws.phase = 0; ws.lane = lane;
+    if (lane == 0) {
+      for (uint32_t i = 0; i < ws.nslot; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws.bars + i * 8), "r"(1) : "memory");
+      mbar_fence_init();
+      for (uint32_t i = 0; i < ws.nslot && ws.bytes_left; ++i) ws.request(smem_u32(ws.ring) + i * ws.chunk_bytes, ws.bars + i * 8);
+    }
+    __syncwarp();
+  }
+  const int vh = p.vh;
+  // float4 index of a segment's u / x arrays inside the staging area (must match tsb_plan.cpp)
+  auto ubase_of = [&](const SegHdr &h, int li) -> int { return h.whole ? 0 : (li & 1) * 2 * vh; };
+  auto xbase_of = [&](const SegHdr &h, int li) -> int { return h.whole ? h.npos : (li & 1) * 2 * vh + vh; };
+
+  // the CTA's segment headers and this warp's block counts, cached in shared memory (plan data: before the wait)
+  SegHdr *segtab = reinterpret_cast<SegHdr *>(smem + off_segtab(stage_bytes, NW, ring));
+  ushort2 *wsegtab = reinterpret_cast<ushort2 *>(smem + off_wsegtab(stage_bytes, NW, ring));
+  {
+    const int nsc = min(cs.y - cs.x, kSegTab);
+    const int4 *src = reinterpret_cast<const int4 *>(p.segs + cs.x);
+    for (int i = tid; i < nsc * 2; i += NT) reinterpret_cast<int4 *>(segtab)[i] = __ldg(src + i);
+    for (int i = tid; i < nsc * NW; i += NT) wsegtab[i] = __ldg(&p.wseg[size_t(cs.x) * NW + i]);
+  }
+  auto seg_at = [&](int s) -> SegHdr { return (s - cs.x < kSegTab) ? segtab[s - cs.x] : p.segs[s]; };
+  auto wseg_at = [&](int s) -> ushort2 { return (s - cs.x < kSegTab) ? wsegtab[(s - cs.x) * NW + warp] : __ldg(&p.wseg[size_t(s) * NW + warp]); };
+  SegHdr hcur{};
+  float px[SV][3];
+  float4 pX[SV];                    // rest position; .w carries the staging position (bit pattern)
+  bool pre = false;                 // (px, pX) hold a prefetched component
+  if (cs.x < cs.y) {
+    hcur = p.segs[cs.x];
+    if (!GLOBAL && !hcur.whole) {   // rest positions of the first component: plan data, loaded before the wait
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < SV; ++k) {
+        const int v = tid + k * NT;
+        if (v < hcur.nv) { pX[k] = __ldg(&p.X4[hcur.x4off + v]); pX[k].w = __uint_as_float(uint32_t(__ldg(&p.pos16[hcur.x4off + v]))); }
+      }
+    }
+  }
+  TSB_STAMP(2);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  TSB_STAMP(3);
+
+  const float gh = p.gradH * (p.gradH_dev ? __ldcg(p.gradH_dev) : 1.f);
+  const float s1 = gh * p.c1, s2 = gh * p.c2;
+  const bool order2 = p.order == 2;
+  float *__restrict__ grad = p.grad;
+  if (grad) {   // vertices no tet references: zero gradient
+    for (int i = blockIdx.x * NT + tid; i < p.n_orphans; i += gridDim.x * NT) {
+      const int v = __ldg(&p.orphans[i]);
+      grad[3 * size_t(v)] = 0.f; grad[3 * size_t(v) + 1] = 0.f; grad[3 * size_t(v) + 2] = 0.f;
+    }
+  }
+
+  double des = 0.0, deb = 0.0;     // per-lane energy partials
+
+  auto load_x = [&](const SegHdr &h) {      // x of a double-buffered component -> registers
 #pragma unroll
-      for (int c = 0; c < 3; ++c) F[r][c] = e[0][r] * a[1][c] + e[1][r] * a[2][c] + e[2][r] * a[3][c];
-    // cofactors = d det / dF  (tet_spheres_cuda.cu:32-46)
-    const float C00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
-    const float C01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
-    const float C02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
-    const float J = F[0][0] * C00 + F[0][1] * C01 + F[0][2] * C02;
-    if (J < 0.f) {   // rare: inverted tet
-      const float m = -J;
-      float coef;
-      if (order == 2) { eb += m * m; coef = 2.f * m; }
-      else { const float m2 = m * m; eb += m2 * m2; coef = 4.f * m2 * m; }
-      if (WITH_GRAD) {
-        float C[3][3];
-        C[0][0] = C00; C[0][1] = C01; C[0][2] = C02;
-        C[1][0] = F[0][2] * F[2][1] - F[0][1] * F[2][2];
-        C[1][1] = F[0][0] * F[2][2] - F[0][2] * F[2][0];
-        C[1][2] = F[0][1] * F[2][0] - F[0][0] * F[2][1];
-        C[2][0] = F[0][1] * F[1][2] - F[0][2] * F[1][1];
-        C[2][1] = F[0][2] * F[1][0] - F[0][0] * F[1][2];
-        C[2][2] = F[0][0] * F[1][1] - F[0][1] * F[1][0];
-        const float pc = -c2 * coef;
+    for (int k = 0; k < SV; ++k) {
+      const int v = tid + k * NT;
+      if (v < h.nv) {
+        const size_t gi = size_t(h.vbase >= 0 ? h.vbase + v : __ldg(&p.vlist[h.x4off + v]));
+        px[k][0] = __ldcg(p.x + 3 * gi); px[k][1] = __ldcg(p.x + 3 * gi + 1); px[k][2] = __ldcg(p.x + 3 * gi + 2);
+      }
+    }
+  };
+  auto store_staged = [&](const SegHdr &h, int li) {
+    float4 *ub = stage + ubase_of(h, li), *xb = stage + xbase_of(h, li);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float P0 = pc * C[r][0], P1 = pc * C[r][1], P2 = pc * C[r][2];
+    for (int k = 0; k < SV; ++k) {
+      const int v = tid + k * NT;
+      if (v < h.nv) {
+        const uint32_t pos = __float_as_uint(pX[k].w);
+        ub[pos] = make_float4(px[k][0] - pX[k].x, px[k][1] - pX[k].y, px[k][2] - pX[k].z, 0.f);
+        xb[pos] = make_float4(px[k][0], px[k][1], px[k][2], 0.f);
+      }
+    }
+  };
+  auto stage_direct = [&](const SegHdr &h, int li) {   // any size, no register prefetch
+    float4 *ub = stage + ubase_of(h, li), *xb = stage + xbase_of(h, li);
+    for (int v = tid; v < h.nv; v += NT) {
+      const float4 X = __ldg(&p.X4[h.x4off + v]);
+      const size_t gi = size_t(h.vbase >= 0 ? h.vbase + v : __ldg(&p.vlist[h.x4off + v]));
+      const float x0 = __ldcg(p.x + 3 * gi), x1 = __ldcg(p.x + 3 * gi + 1), x2 = __ldcg(p.x + 3 * gi + 2);
+      const uint32_t pos = __ldg(&p.pos16[h.x4off + v]);
+      ub[pos] = make_float4(x0 - X.x, x1 - X.y, x2 - X.z, 0.f);
+      xb[pos] = make_float4(x0, x1, x2, 0.f);
+    }
+  };
+
+  if (!GLOBAL) {
+    if (cs.x < cs.y) {
+      if (hcur.whole) stage_direct(hcur, 0);
+      else { load_x(hcur); store_staged(hcur, 0); }
+    }
+    __syncthreads();
+    TSB_STAMP(4);
+  } else {
+    __syncthreads();      // segment tables visible
+  }
+  ws.begin();
+  TSB_STAMP(12);
+
+  for (int s = cs.x; s < cs.y; ++s) {
+    const int li = s - cs.x;
+    // ---- prefetch the next component's x / X into registers (lands during this segment's math)
+    SegHdr hn{};
+    const ushort2 wseg = wseg_at(s);
+    pre = false;
+    if (s + 1 < cs.y) {
+      hn = seg_at(s + 1);
+      if (!GLOBAL) {
+        pre = !hcur.whole && !hn.whole;
+        if (pre) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) z[j][r] = P0 * a[j + 1][0] + P1 * a[j + 1][1] + P2 * a[j + 1][2];
+          for (int k = 0; k < SV; ++k) {
+            const int v = tid + k * NT;
+            if (v < hn.nv) { pX[k] = __ldg(&p.X4[hn.x4off + v]); pX[k].w = __uint_as_float(uint32_t(__ldg(&p.pos16[hn.x4off + v]))); }
+          }
+          load_x(hn);
         }
       }
     }
-  }
 
-  // smoothness stencil: H = w * sum_k rho_k d_k (x) a_k      (branch-free; boundary faces have
-  // rho = 0 and gather the tet's own vertex)
-  float H[3][3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) { H[r][0] = 0.f; H[r][1] = 0.f; H[r][2] = 0.f; }
-  float lam[4][3], rho[4];
-  int deg = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool valid = (ioppr[k] & 0x8000u) != 0u;
-    deg += valid ? 1 : 0;
-    const float rx = po[k].w - p0.w, ry = qo[k].x - q0.x, rz = qo[k].y - q0.y;
-    const float l1 = b[0] * rx + b[1] * ry + b[2] * rz;
-    const float l2 = b[3] * rx + b[4] * ry + b[5] * rz;
-    const float l3 = b[6] * rx + b[7] * ry + b[8] * rz;
-    const float lkk = (k == 0) ? (1.f - l1 - l2 - l3) : (k == 1 ? l1 : (k == 2 ? l2 : l3));
-    const float rk = valid ? __fdividef(-1.f, lkk) : 0.f;
-    lam[k][0] = l1; lam[k][1] = l2; lam[k][2] = l3; rho[k] = rk;
-    const float dx = (po[k].x - p0.x) - l1 * e[0][0] - l2 * e[1][0] - l3 * e[2][0];
-    const float dy = (po[k].y - p0.y) - l1 * e[0][1] - l2 * e[1][1] - l3 * e[2][1];
-    const float dz = (po[k].z - p0.z) - l1 * e[0][2] - l2 * e[1][2] - l3 * e[2][2];
-    const float sx = rk * dx, sy = rk * dy, sz = rk * dz;
-    H[0][0] += sx * a[k][0]; H[0][1] += sx * a[k][1]; H[0][2] += sx * a[k][2];
-    H[1][0] += sy * a[k][0]; H[1][1] += sy * a[k][1]; H[1][2] += sy * a[k][2];
-    H[2][0] += sz * a[k][0]; H[2][1] += sz * a[k][1]; H[2][2] += sz * a[k][2];
-  }
-  const float w = (lscale && deg > 0) ? __fdividef(1.f, float(deg)) : 1.f;
-  float hh = 0.f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { H[r][c] *= w; hh += H[r][c] * H[r][c]; }
-  es += 0.5f * hh;
+    // gather of a staged float4.  STAGED: j is a byte offset from the start of shared memory (the plan
+    // bakes the segment's half-buffer into it); GLOBAL: j is a vertex id.
+    auto gatherU = [&](uint32_t j) -> float4 { return GLOBAL ? __ldg(p.u4g + j) : *reinterpret_cast<const float4 *>(smem + j); };
+    auto gatherX = [&](uint32_t j) -> float4 { return GLOBAL ? __ldg(p.x4g + j) : *reinterpret_cast<const float4 *>(smem + j); };
+    const int xb16 = GLOBAL ? 0 : xbase_of(hcur, li) * 16;
+    auto gid_x = [&](uint32_t j) -> size_t {
+      if (GLOBAL) return size_t(j);
+      return size_t(__ldg(&p.pos_gid[hcur.p4off + ((j - uint32_t(xb16)) >> 4)]));
+    };
+    // reference displacement of the component: sum_i g_i = 0, so 1/2 sum_i (u_i - uref).g_i is the same
+    // energy with the rigid translation taken out of the cancellation
+    const float4 uref = GLOBAL ? __ldg(p.u4g + hcur.x4off) : stage[ubase_of(hcur, li)];
+    if (s == cs.x) TSB_STAMP(13);
 
-  if (WITH_GRAD) {
-    const float cw = c1 * w;
-    float ys[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float sk = cw * rho[k];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float y = sk * (H[r][0] * a[k][0] + H[r][1] * a[k][1] + H[r][2] * a[k][2]);
-        outb[((4 + k) * 3 + r) * TTP + lt] = y;
-        ys[r] += y;
-        z[0][r] -= lam[k][0] * y; z[1][r] -= lam[k][1] * y; z[2][r] -= lam[k][2] * y;
+    // ---- operator rows: L lanes per vertex row (header in slot 0 of the first quad) ------------------
+    for (int rb = 0; rb < int(wseg.x); ++rb) {
+      const uint32_t hdr = *reinterpret_cast<const uint32_t *>(ws.cell + WOFF + lane * 16);
+      const uint32_t rid = hdr & 0xFFFFFFu, len4 = (hdr >> 24) & 63u, llog = hdr >> 30;   // global row id | quads | log2(lanes per row)
+      const bool active = rid != 0xFFFFFFu;
+      const uint32_t rowj = GLOBAL ? *reinterpret_cast<const uint32_t *>(ws.cell + lane * 16)
+                                   : uint32_t(*reinterpret_cast<const uint16_t *>(ws.cell + lane * 8));
+      const float4 ui = gatherU(rowj);
+      f32x2 AX = 0ull, AY = 0ull, AZ = 0ull;     // (even-entry, odd-entry) partial sums
+      uint32_t left = len4;
+      while (left) {
+        const uint32_t n = min(left, ws.avail());
+        const unsigned char *cp = ws.cell + lane * 4 * F::IB;
+#pragma unroll 2
+        for (uint32_t q = 0; q < n; ++q, cp += CELL) {
+          uint32_t j[4];
+          if (GLOBAL) {
+            const uint4 qi = *reinterpret_cast<const uint4 *>(cp);
+            j[0] = qi.x; j[1] = qi.y; j[2] = qi.z; j[3] = qi.w;
+          } else {
+            const uint2 qi = *reinterpret_cast<const uint2 *>(cp);
+            j[0] = qi.x & 0xFFFFu; j[1] = qi.x >> 16; j[2] = qi.y & 0xFFFFu; j[3] = qi.y >> 16;
+          }
+          const float4 qw = *reinterpret_cast<const float4 *>(cp + WOFF + lane * (16 - 4 * F::IB));
+          const float4 u0 = gatherU(j[0]), u1 = gatherU(j[1]), u2 = gatherU(j[2]), u3 = gatherU(j[3]);
+          const f32x2 W01 = pk2(qw.x, qw.y), W23 = pk2(qw.z, qw.w);
+          fma2_acc(AX, W01, pk2(u0.x - ui.x, u1.x - ui.x));
+          fma2_acc(AY, W01, pk2(u0.y - ui.y, u1.y - ui.y));
+          fma2_acc(AZ, W01, pk2(u0.z - ui.z, u1.z - ui.z));
+          fma2_acc(AX, W23, pk2(u2.x - ui.x, u3.x - ui.x));
+          fma2_acc(AY, W23, pk2(u2.y - ui.y, u3.y - ui.y));
+          fma2_acc(AZ, W23, pk2(u2.z - ui.z, u3.z - ui.z));
+        }
+        ws.advance(n);
+        left -= n;
+      }
+#ifdef TSB_TRACE
+      if (s == cs.x && rb == 0) { TSB_STAMP(14); if (tid == 0 && p.trace) p.trace[blockIdx.x * 16 + 15] = len4 | (uint32_t(wseg.x) << 16) | (uint32_t(wseg.y) << 24); }
+#endif
+      float ax = sum2(AX), ay = sum2(AY), az = sum2(AZ);
+      for (uint32_t o = 1; o < (1u << llog); o <<= 1) {   // the L lanes of a row are adjacent
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
+      }
+      if (active && (lane & ((1u << llog) - 1u)) == 0) {
+        des += double(fmaf(ui.x - uref.x, ax, fmaf(ui.y - uref.y, ay, (ui.z - uref.z) * az)));
+        if (grad) {
+          const size_t gi = rid;
+          grad[3 * gi] = s1 * ax; grad[3 * gi + 1] = s1 * ay; grad[3 * gi + 2] = s1 * az;
+        }
       }
     }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      outb[(0 * 3 + r) * TTP + lt] = -(z[0][r] + z[1][r] + z[2][r] + ys[r]);   // translation invariance
-      outb[(1 * 3 + r) * TTP + lt] = z[0][r];
-      outb[(2 * 3 + r) * TTP + lt] = z[1][r];
-      outb[(3 * 3 + r) * TTP + lt] = z[2][r];
-    }
-  }
-}
-
-// Tile kernel: persistent CTAs (MINB per SM), each looping over tiles b, b+G, b+2G, ...  The three
-// phases of a tile run in lock-step inside the CTA (they are all shared-memory heavy, so overlapping
-// them only makes them contend -- profiles/r01_summary.md), but every global access of tile j+1 is
-// in flight while tile j computes:
-//   * vertex blob j+1 (double buffered) is requested by TMA as soon as tile j-1 has been consumed,
-//   * tet blob j+1 the moment the tet math of tile j is done, the gather table of tile j right after
-//     the row gather of tile j-1,
-//   * the only dependent chain, vertex id -> x, is issued straight from global memory one phase ahead
-//     (ids at the top of tile j, x right after its tet math) and lands in registers.
-template <int TT, int NV, int NT, int MINB, bool WITH_GRAD>
-__global__ void __launch_bounds__(NT, MINB) energy_grad_kernel(const __grid_constant__ KParams p) {
-  using L = Smem<TT, NV>;
-  constexpr int NR = L::NR, TTP = L::kTTP;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint4 *idx_s = reinterpret_cast<const uint4 *>(smem_raw + L::kTOff);
-  const float *B_s = reinterpret_cast<const float *>(smem_raw + L::kTOff + 16 * TT);
-  const uint16_t *ell_s = reinterpret_cast<const uint16_t *>(smem_raw + L::kEllOff);
-  float4 *xs4 = reinterpret_cast<float4 *>(smem_raw + L::kXs4Off);                               // x, y, z, X
-  float *outb = reinterpret_cast<float *>(smem_raw + L::kOutOff);
-  __shared__ __align__(8) uint64_t bar_v[2], bar_t, bar_e;
-  __shared__ float s_red[2 * (NT / 32)];
-
-  const int tid = threadIdx.x;
-  const int G = int(gridDim.x);
-  const int n_my = (p.n_tiles - int(blockIdx.x) + G - 1) / G;
-  const uint32_t nt_b = uint32_t(p.fill);
-  constexpr int kVPer = (NV + NT - 1) / NT;
-
-  auto issue_v = [&](int j) {
-    const int tile = int(blockIdx.x) + j * G;
-    mbar_expect_tx(&bar_v[j & 1], L::kVBytes);
-    bulk_g2s(smem_raw + (j & 1) * L::kVStage, p.vblob + size_t(tile) * L::kVBytes, L::kVBytes, &bar_v[j & 1]);
-  };
-  auto issue_t = [&](int j) {
-    const int tile = int(blockIdx.x) + j * G;
-    mbar_expect_tx(&bar_t, 52u * nt_b);
-    const unsigned char *tb = p.tblob + size_t(tile) * (52 * TT);
-    bulk_g2s(smem_raw + L::kTOff, tb, 16u * nt_b, &bar_t);
-    bulk_g2s(smem_raw + L::kTOff + 16 * TT, tb + 16 * TT, 36u * nt_b, &bar_t);
-  };
-  auto issue_e = [&](const int2 el) {
-    mbar_expect_tx(&bar_e, 2u * uint32_t(el.y));
-    if (el.y > 0) bulk_g2s(smem_raw + L::kEllOff, p.ell + el.x, 2u * uint32_t(el.y), &bar_e);
-  };
-  // TMA is issued by the LAST thread: its warp processes the fewest tets of a tile, so the issue
-  // latency stays off the critical path of the tet math.
-  const bool issuer = (tid == NT - 1);
-  auto load_vids = [&](int j, int (&vid)[kVPer]) {     // entries past nvert are zero padding (-> x[0])
-    const int32_t *vl_g = reinterpret_cast<const int32_t *>(p.vblob + size_t(int(blockIdx.x) + j * G) * L::kVBytes + 64);
-#pragma unroll
-    for (int q = 0; q < kVPer; ++q) vid[q] = (tid + q * NT < NV) ? __ldg(vl_g + tid + q * NT) : 0;
-  };
-  auto load_x = [&](const int (&vid)[kVPer], float (&px)[kVPer][3]) {
-#pragma unroll
-    for (int q = 0; q < kVPer; ++q) {
-      const float *xp = p.x + 3 * size_t(vid[q]);
-      px[q][0] = __ldg(xp); px[q][1] = __ldg(xp + 1); px[q][2] = __ldg(xp + 2);
-    }
-  };
-
-  int vid[kVPer];
-  float px[kVPer][3];
-  if (n_my > 0) load_vids(0, vid);
-  if (issuer) {
-    mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1); mbar_init(&bar_t, 1); mbar_init(&bar_e, 1);
-    mbar_fence_init();
-    if (n_my > 0) { issue_v(0); issue_t(0); }
-  }
-  if (WITH_GRAD && tid < 3) outb[tid * TTP + TT] = 0.f;   // zero column for gather-table padding
-  // Everything above touches only plan data.  x (may have been updated by the optimiser), the scratch
-  // slots and the energy partials belong to the previous kernels in the stream: wait for them here.
-  // (The kernel is launched with programmatic stream serialisation, so this prologue overlaps the
-  // tail of the previous combine kernel.)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (n_my > 0) load_x(vid, px);
-  __syncthreads();
-
-  float es = 0.f, eb = 0.f;
-  const float c1 = p.c1, c2 = p.c2;
-  const int order = p.order;
-  const bool lscale = p.laplacian_scale != 0;
-  for (int j = 0; j < n_my; ++j) {
-    const unsigned char *vb = smem_raw + (j & 1) * L::kVStage;
-    const TileHeader *hd = reinterpret_cast<const TileHeader *>(vb);
-    const float *Xx_s = reinterpret_cast<const float *>(vb + 64 + 4 * NV);
-    const float2 *xs2 = reinterpret_cast<const float2 *>(vb + 64 + 8 * NV);                      // (Y, Z) rest
-    const int32_t *slot_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV);
-    const int32_t *grp_s = reinterpret_cast<const int32_t *>(vb + 64 + 16 * NV + 4 * NR);
-    if (j + 1 < n_my) load_vids(j + 1, vid);           // ids of the next tile: needed only after this tile's tet math
-    int2 el = make_int2(0, 0);
-    if (WITH_GRAD && issuer) el = __ldg(p.tile_ell + int(blockIdx.x) + j * G);   // consumed after (A): latency hidden
-
-    // ---------------- phase 0: x (already in registers) + rest X -> shared -------------------
-    mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
-    const int ntet = hd->ntet, nvert = hd->nvert, nrow = hd->nrow;
-#pragma unroll
-    for (int q = 0; q < kVPer; ++q) {
-      const int i = tid + q * NT;
-      if (i < nvert) xs4[i] = make_float4(px[q][0], px[q][1], px[q][2], Xx_s[i]);
-    }
-    __syncthreads();     // (A) xs4 complete; every thread has left the previous tile's row gather
-    if (issuer) {
-      if (j + 1 < n_my) issue_v(j + 1);               // its stage held tile j-1, now fully consumed
-      if (WITH_GRAD) issue_e(el);                      // gather-table buffer is free since (A)
-    }
-
-    // ---------------- phase 1: tets -----------------------------------------------------------------
-    mbar_wait(&bar_t, j & 1);
-    for (int lt = tid; lt < ntet; lt += NT)
-      tet_body<TTP, WITH_GRAD>(lt, idx_s, B_s, xs4, xs2, outb, c1, c2, order, lscale, es, eb);
-    __syncthreads();     // (B) output table complete; tet blob and xs4 are free
-    if (j + 1 < n_my) {
-      if (issuer) issue_t(j + 1);
-      load_x(vid, px);                                 // lands while the row gather below runs
-    } else {
-      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // last tile: let the combine kernel launch
-    }
-
-    // ---------------- phase 2: per-row gather --------------------------------------------------------
-    if (WITH_GRAD) {
-      mbar_wait(&bar_e, j & 1);
-      float4 *scratch4 = reinterpret_cast<float4 *>(p.scratch);
-      for (int r = tid; r < nrow; r += NT) {
-        const int g = r >> 5, lane = r & 31;
-        const int beg = grp_s[g], end = grp_s[g + 1];
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        gather_vertex<TTP>(outb, reinterpret_cast<const uint32_t *>(ell_s + beg) + lane, (end - beg) >> 6, g0, g1, g2);
-        scratch4[slot_s[r]] = make_float4(g0, g1, g2, 0.f);
+    if (s == cs.x) TSB_STAMP(5);
+    if (grad) {   // all warps' rows of this segment are stored -> ONE release of the component's counter, sent by
+                  // the last warp (which owns no tets, so it never waits on its own signal)
+      if (warp == NW - 1) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        if (lane == 0) { __threadfence(); atomicAdd(p.done + hcur.comp, 1u); }
+      } else {
+        asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
       }
     }
+
+    // ---- barrier: TPL tets per lane ---------------------------------------------------------------------
+    bool waited = false;
+    for (int tc = 0; tc < int(wseg.y); ++tc) {
+      uint32_t tj[F::TPL][4];
+      float tdet[F::TPL];
+      if (GLOBAL) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(ws.cell + lane * 16);
+        tj[0][0] = a.x; tj[0][1] = a.y; tj[0][2] = a.z; tj[0][3] = a.w;
+        tdet[0] = *reinterpret_cast<const float *>(ws.cell + 512 + lane * 4);
+      } else {
+        const uint4 a = *reinterpret_cast<const uint4 *>(ws.cell + lane * 16);
+        const float2 d = *reinterpret_cast<const float2 *>(ws.cell + 512 + lane * 8);
+        tj[0][0] = a.x & 0xFFFFu; tj[0][1] = a.x >> 16; tj[0][2] = a.y & 0xFFFFu; tj[0][3] = a.y >> 16;
+        tj[F::TPL - 1][0] = a.z & 0xFFFFu; tj[F::TPL - 1][1] = a.z >> 16; tj[F::TPL - 1][2] = a.w & 0xFFFFu; tj[F::TPL - 1][3] = a.w >> 16;
+        tdet[0] = d.x; tdet[F::TPL - 1] = d.y;
+      }
+      float4 xv[F::TPL][4];
+#pragma unroll
+      for (int t = 0; t < int(F::TPL); ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[t][k] = gatherX(tj[t][k]);
+      ws.advance(1);
+#pragma unroll
+      for (int t = 0; t < int(F::TPL); ++t) {
+        const float4 x0 = xv[t][0], x1 = xv[t][1], x2 = xv[t][2], x3 = xv[t][3];
+        const float idet = tdet[t];
+        const float e1x = x1.x - x0.x, e1y = x1.y - x0.y, e1z = x1.z - x0.z;
+        const float e2x = x2.x - x0.x, e2y = x2.y - x0.y, e2z = x2.z - x0.z;
+        const float e3x = x3.x - x0.x, e3y = x3.y - x0.y, e3z = x3.z - x0.z;
+        const float c1x = e2y * e3z - e2z * e3y, c1y = e2z * e3x - e2x * e3z, c1z = e2x * e3y - e2y * e3x;   // e2 x e3
+        const float J = (e1x * c1x + e1y * c1y + e1z * c1z) * idet;
+        if (J < 0.f) {
+          const float m = -J, m2 = m * m;
+          deb += double(order2 ? m2 : m2 * m2);
+          if (grad) {
+            const float coef = order2 ? 2.f * m : 4.f * m2 * m;       // p (-J)^(p-1)
+            const float k = -coef * idet * s2;                         // gradH c2 dphi/dJ / det(Dm)
+            const float g1x = k * c1x, g1y = k * c1y, g1z = k * c1z;
+            const float g2x = k * (e3y * e1z - e3z * e1y), g2y = k * (e3z * e1x - e3x * e1z), g2z = k * (e3x * e1y - e3y * e1x);
+            const float g3x = k * (e1y * e2z - e1z * e2y), g3y = k * (e1z * e2x - e1x * e2z), g3z = k * (e1x * e2y - e1y * e2x);
+            if (!waited) {   // every row of this component must be stored before we add to it
+              const unsigned int need = unsigned(hcur.expected);
+              while (ld_acquire(p.done + hcur.comp) < need) __nanosleep(40);
+              waited = true;
+            }
+            const size_t v0 = 3 * gid_x(tj[t][0]), v1 = 3 * gid_x(tj[t][1]), v2 = 3 * gid_x(tj[t][2]), v3 = 3 * gid_x(tj[t][3]);
+            atomicAdd(grad + v0, -(g1x + g2x + g3x)); atomicAdd(grad + v0 + 1, -(g1y + g2y + g3y)); atomicAdd(grad + v0 + 2, -(g1z + g2z + g3z));
+            atomicAdd(grad + v1, g1x); atomicAdd(grad + v1 + 1, g1y); atomicAdd(grad + v1 + 2, g1z);
+            atomicAdd(grad + v2, g2x); atomicAdd(grad + v2 + 1, g2y); atomicAdd(grad + v2 + 2, g2z);
+            atomicAdd(grad + v3, g3x); atomicAdd(grad + v3 + 1, g3y); atomicAdd(grad + v3 + 2, g3z);
+          }
+        }
+      }
+    }
+    if (s == cs.x) TSB_STAMP(6);
+
+    // ---- hand the staging buffers over ------------------------------------------------------------------
+    if (!GLOBAL) {
+      if (pre) store_staged(hn, li + 1);
+      __syncthreads();
+      if (s + 1 < cs.y && !pre) {
+        stage_direct(hn, li + 1);
+        __syncthreads();
+      }
+    } else if (grad) {
+      __syncthreads();     // keeps the named barrier's generations apart
+    }
+    hcur = hn;
   }
 
-  // one (smooth, barrier) partial per CTA (tree reduction; the cross-CTA sum is done in fp64 by the combine kernel)
-  {
-    const float ws = warp_sum(es), wb = warp_sum(eb);
-    if ((tid & 31) == 0) { s_red[tid >> 5] = ws; s_red[NT / 32 + (tid >> 5)] = wb; }
-  }
+  // ---- energies: lanes -> warp -> CTA partial; CTA 0 folds all partials in fixed order ---------------------
+  TSB_STAMP(7);
+  des = warp_sum(des);
+  deb = warp_sum(deb);
+  if (lane == 0) { red[2 * warp] = des; red[2 * warp + 1] = deb; }
   __syncthreads();
-  if (tid < 32) {
-    float vs = (tid < NT / 32) ? s_red[tid] : 0.f, vb2 = (tid < NT / 32) ? s_red[NT / 32 + tid] : 0.f;
-    vs = warp_sum(vs); vb2 = warp_sum(vb2);
-    if (tid == 0) { p.tile_energy[2 * blockIdx.x] = vs; p.tile_energy[2 * blockIdx.x + 1] = vb2; }
+  TSB_STAMP(8);
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < NW; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+    a *= 0.5;
+    // one 16-byte store carries the pair; its arrival IS the "this CTA is done" signal (no fence, no ticket)
+    unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+    if (ua == kSentinel) ua = 0x7FF8000000000000ull;
+    if (ub == kSentinel) ub = 0x7FF8000000000000ull;
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 2 * blockIdx.x), "l"(ua), "l"(ub) : "memory");
   }
-  if (n_my == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  TSB_STAMP(9);
+  if (blockIdx.x == 0 && warp == 0) {
+    __syncwarp();
+    double a = 0.0, b = 0.0;
+    for (int c = lane; c < int(gridDim.x); c += 32) {
+      unsigned long long ua, ub;
+      do {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(p.cta_energy + 2 * c) : "memory");
+      } while (ua == kSentinel || ub == kSentinel);
+      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 2 * c), "l"(kSentinel), "l"(kSentinel) : "memory");   // re-arm
+      a += __longlong_as_double((long long)ua);
+      b += __longlong_as_double((long long)ub);
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) {
+      p.energy_out[0] = float(double(p.c1) * a + double(p.c2) * b);
+      p.energy_out[1] = float(a);
+      p.energy_out[2] = float(b);
+    }
+    for (int c = lane; c < p.n_components; c += 32) p.done[c] = 0u;   // every CTA has finished: safe to re-arm
+  }
+  TSB_STAMP(10);
+#ifdef TSB_TRACE
+  if (tid == 0 && p.trace) p.trace[blockIdx.x * 16 + 11] = gtime();
+#endif
 }
 
-// Combine kernel: grad[v] = gradH * sum of v's scratch slots (fixed order); block 0 also folds the
-// per-tile energies in fp64.  Launched with programmatic stream serialization right behind the
-// tile kernel; griddepcontrol.wait blocks until that grid has completed and flushed.
-template <int NT>
-__global__ void __launch_bounds__(NT) combine_kernel(const __grid_constant__ KParams p, int n_vertices, const int32_t *__restrict__ slot_ptr) {
-  const int tid = threadIdx.x;
-  const int v = blockIdx.x * NT + tid;
-  int s0 = 0, s1 = 0;
-  if (v < n_vertices) { s0 = __ldg(slot_ptr + v); s1 = __ldg(slot_ptr + v + 1); }   // plan data: safe before the wait
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next tile kernel may start its prologue
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  float gh = p.gradH;
-  if (p.gradH_dev) gh *= __ldg(p.gradH_dev);   // produced by earlier kernels in the stream: read after the wait
-  if (v < n_vertices) {
-    const float4 *scratch4 = reinterpret_cast<const float4 *>(p.scratch);
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    // slots are summed in index order (deterministic); loads are issued 4 at a time so the L2 round
-    // trips overlap instead of forming a dependent chain
-    for (int s = s0; s < s1; s += 4) {
-      float4 q[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) q[j] = (s + j < s1) ? __ldcg(scratch4 + s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { g0 += q[j].x; g1 += q[j].y; g2 += q[j].z; }
-    }
-    float *gp = p.grad + 3 * size_t(v);
-    gp[0] = gh * g0; gp[1] = gh * g1; gp[2] = gh * g2;
-  }
-  if (blockIdx.x == 0) {
-    double as = 0.0, ab = 0.0;
-    for (int t = tid; t < p.n_energy; t += NT) { as += double(__ldcg(p.tile_energy + 2 * t)); ab += double(__ldcg(p.tile_energy + 2 * t + 1)); }
-    as = warp_sum(as); ab = warp_sum(ab);
-    __shared__ double s_dred[2 * (NT / 32)];
-    if ((tid & 31) == 0) { s_dred[tid >> 5] = as; s_dred[NT / 32 + (tid >> 5)] = ab; }
-    __syncthreads();
-    if (tid == 0) {
-      double ts = 0.0, tb = 0.0;
-      for (int wgt = 0; wgt < NT / 32; ++wgt) { ts += s_dred[wgt]; tb += s_dred[NT / 32 + wgt]; }
-      p.energy_out[0] = float(double(p.c1) * ts + double(p.c2) * tb);
-      p.energy_out[1] = float(ts);
-      p.energy_out[2] = float(tb);
-    }
+// GLOBAL mode pre-pass: u = x - X and x as float4 per vertex.
+__global__ void prestage_kernel(const float *__restrict__ x, const float4 *__restrict__ X4, float4 *__restrict__ u4,
+                                float4 *__restrict__ x4, int n) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+    const float4 X = X4[v];
+    const float a = x[3 * size_t(v)], b = x[3 * size_t(v) + 1], c = x[3 * size_t(v) + 2];
+    u4[v] = make_float4(a - X.x, b - X.y, c - X.z, 0.f);
+    x4[v] = make_float4(a, b, c, 0.f);
   }
 }
 
@@ -514,121 +582,70 @@ __global__ void adam_uniform_apply_kernel(float *__restrict__ p, const float *__
   }
 }
 
-// Compiled variants: tile capacity TT -> staged-vertex capacity NV (then threads, min CTAs/SM)
-#define TSB_V256 256, 256
-#define TSB_V512 512, 256
-#define TSB_V1024 1024, 640
-
-cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
-int g_num_sms = 148;
-
-template <int TT, int NV, int NT, int MINB>
-cudaError_t launch_variant(const KParams &p0, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
-  KParams p = p0;
-  p.exp_flags = g_exp_flags;
-  const int slots = MINB * g_num_sms;
-  const int grid = p.n_tiles < slots ? p.n_tiles : slots;
-  p.n_energy = grid;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(grid));
-  cfg.blockDim = dim3(NT);
-  cfg.dynamicSmemBytes = Smem<TT, NV>::kBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_tile ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = p.grad ? cudaLaunchKernelEx(&cfg, energy_grad_kernel<TT, NV, NT, MINB, true>, p)
-                         : cudaLaunchKernelEx(&cfg, energy_grad_kernel<TT, NV, NT, MINB, false>, p);
-  if (e != cudaSuccess || g_skip_combine) return e;
-  return launch_combine(p, n_vertices, slot_ptr, stream);
+inline int grid_for(int64_t count, int block) {
+  int64_t g = (count + block - 1) / block;
+  return int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 
-// combine kernel, chained with programmatic dependent launch
-cudaError_t launch_combine(const KParams &p, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
-  constexpr int CNT = 256;
-  const int nv = p.grad ? n_vertices : 0;
+template <int NW, int MINB, bool GLOBAL>
+cudaError_t launch_variant(const KParams &p, const LaunchConfig &lc, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(nv > 0 ? (nv + CNT - 1) / CNT : 1));
-  cfg.blockDim = dim3(CNT);
-  cfg.dynamicSmemBytes = 0;
+  cfg.gridDim = dim3(unsigned(lc.grid));
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = size_t(lc.smem_bytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, combine_kernel<CNT>, p, nv, slot_ptr);
+  return cudaLaunchKernelEx(&cfg, energy_grad_kernel<NW, MINB, GLOBAL>, p);
 }
 
-template <int TT, int NV, int NT, int MINB>
-cudaError_t prepare_variant() {
-  const int smem = Smem<TT, NV>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<TT, NV, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(energy_grad_kernel<TT, NV, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-}
-
-inline int grid_for(int64_t count, int block) {
-  int64_t g = (count + block - 1) / block;
-  return int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+template <int NW, int MINB, bool GLOBAL>
+cudaError_t occupancy_variant(int smem_bytes, int *ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) { *ctas_per_sm = 0; cudaGetLastError(); return cudaSuccess; }   // does not fit
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, energy_grad_kernel<NW, MINB, GLOBAL>, NW * 32, size_t(smem_bytes));
 }
 
 }  // namespace
 
-int nvmax_for(int tile_tets) {
-  switch (tile_tets) {
-    case 256: return 256;
-    case 512: return 256;
-    case 1024: return 640;
-  }
-  return 0;
+int energy_ring_bytes(int slots, int cells_per_chunk, bool global) { return slots * cells_per_chunk * (global ? kCellGlobal : kCellStaged); }
+
+int energy_smem_bytes(int nw, int ring_slots, int cells_per_chunk, int area_verts, bool global) {
+  return smem_total(global ? 0 : area_verts * 32, nw, energy_ring_bytes(ring_slots, cells_per_chunk, global));
 }
 
-static int g_threads_512 = 256;
-
-cudaError_t prepare_energy_grad(int tile_tets) {
-  {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
-  }
-  switch (tile_tets) {
-    case 256: return prepare_variant<TSB_V256, 256, 3>();
-    case 512: {
-      cudaError_t e = prepare_variant<TSB_V512, 256, 2>();
-      if (e != cudaSuccess) return e;
-      return prepare_variant<TSB_V512, 512, 1>();
-    }
-    case 1024: return prepare_variant<TSB_V1024, 512, 1>();
-  }
+cudaError_t energy_occupancy(int nw, int smem_bytes, bool global, int *ctas_per_sm) {
+  if (nw == 16) return global ? occupancy_variant<16, 1, true>(smem_bytes, ctas_per_sm) : occupancy_variant<16, 1, false>(smem_bytes, ctas_per_sm);
+  if (nw == 8) return global ? occupancy_variant<8, 2, true>(smem_bytes, ctas_per_sm) : occupancy_variant<8, 2, false>(smem_bytes, ctas_per_sm);
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream) {
-  switch (tile_tets) {
-    case 256: return launch_variant<TSB_V256, 256, 3>(p, n_vertices, slot_ptr, stream);
-    case 512:
-      return g_threads_512 == 512 ? launch_variant<TSB_V512, 512, 1>(p, n_vertices, slot_ptr, stream) : launch_variant<TSB_V512, 256, 2>(p, n_vertices, slot_ptr, stream);
-    case 1024: return launch_variant<TSB_V1024, 512, 1>(p, n_vertices, slot_ptr, stream);
+cudaError_t launch_energy_grad(const KParams &p, const LaunchConfig &lc, cudaStream_t stream) {
+  if (lc.global) {
+    prestage_kernel<<<grid_for(p.n, 256), 256, 0, stream>>>(p.x, p.X4, p.u4g, p.x4g, p.n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (lc.nw == 16) return launch_variant<16, 1, true>(p, lc, stream);
+    if (lc.nw == 8) return launch_variant<8, 2, true>(p, lc, stream);
+    return cudaErrorInvalidValue;
   }
+  if (lc.nw == 16) return launch_variant<16, 1, false>(p, lc, stream);
+  if (lc.nw == 8) return launch_variant<8, 2, false>(p, lc, stream);
   return cudaErrorInvalidValue;
 }
-
-void set_threads_512(int nt) { g_threads_512 = (nt == 512) ? 512 : 256; }
-void set_skip_combine(int v) { g_skip_combine = v; }
-void set_pdl_tile(int v) { g_pdl_tile = v; }
-void set_exp_flags(int v) { g_exp_flags = v; }
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s) {
   scale_kernel<<<grid_for(count, 256), 256, 0, s>>>(g, count, gradH, gradH_dev, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st) {
+cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work4, cudaStream_t st) {
   const int grid = grid_for(count, 256);
-  absmax_kernel<<<grid, 256, 0, st>>>(g, count, work2);
-  grad_limit_apply_kernel<<<grid, 256, 0, st>>>(g, count, thr, s, work2);
+  absmax_kernel<<<grid, 256, 0, st>>>(g, count, work4);
+  grad_limit_apply_kernel<<<grid, 256, 0, st>>>(g, count, thr, s, work4);
   return cudaGetLastError();
 }
 

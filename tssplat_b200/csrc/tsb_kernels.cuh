@@ -10,13 +10,22 @@ namespace tsb {
 
 struct KParams {
   // plan (read-only, built once by tsb_create)
-  const unsigned char *vblob;   // n_tiles * vblob_bytes(NV)
-  const unsigned char *tblob;   // n_tiles * tblob_bytes(TT)
-  const uint16_t *ell;          // gather tables
-  const int2 *tile_ell;         // (ell_off, nell) per tile
-  // per-handle scratch
-  float *scratch;               // [4*n_slots] per-(tile,vertex) partial gradients (float4)
-  float *tile_energy;           // [2*n_energy] (smooth, barrier) partials: per tile (v4) or per CTA (pipelined)
+  const unsigned char *stream;  // per-warp byte streams (operator rows + tet blocks)
+  const float4 *X4;             // rest positions, float4 per staged vertex (STAGED: component-major; GLOBAL: by vertex id)
+  const int32_t *vlist;         // STAGED: global vertex id per staged vertex (used when a component is not contiguous)
+  const uint16_t *pos16;        // STAGED: staging position per staged vertex (bank-aware placement)
+  const int32_t *pos_gid;       // STAGED: global vertex id per staging position
+  const SegHdr *segs;
+  const int2 *cta_seg;          // per CTA: [first segment, one past last)
+  const uint2 *wdesc;           // per (CTA, warp): (stream offset / 16, stream bytes)
+  const ushort2 *wseg;          // per (segment, warp): (row blocks, tet blocks)
+  const int32_t *orphans;       // vertices without tets
+  int32_t n_orphans;
+  int32_t n_components;
+  // per-handle scratch (self-resetting)
+  unsigned int *done;           // [n_components] warps that have stored their rows of a component
+  double *cta_energy;           // [2*grid] (smooth, barrier) partial per CTA; a NaN-payload sentinel = "not written yet"
+  float4 *u4g, *x4g;            // GLOBAL mode: displacement / position per vertex (written by the pre-pass)
   // per launch
   const float *x;               // [3n]
   float *grad;                  // [3n] or nullptr (energy only)
@@ -24,27 +33,34 @@ struct KParams {
   const float *gradH_dev;       // optional device scalar
   float c1, c2, gradH;
   int32_t order;                // 2 or 4
-  int32_t laplacian_scale;
-  int32_t n_tiles;
-  int32_t n_energy;             // number of (smooth, barrier) partials the tile kernel writes
-  int32_t fill;                 // tets per tile upper bound (sizes the tet-blob TMA copy)
-  int32_t exp_flags;            // developer A/B switches (0 in production)
+  int32_t n;                    // vertices
+  int32_t vh;                   // STAGED: half-buffer capacity in vertices
+  int32_t ring_bytes;           // per-warp ring size = slots * cells_per_chunk cells
+  int32_t cells_per_chunk;      // cells per TMA bulk copy (= per ring slot)
+  int32_t stage_bytes;          // STAGED: bytes of the staging area at the start of shared memory
+#ifdef TSB_TRACE
+  unsigned long long *trace;    // profiling build only: [grid][16] phase stamps
+#endif
 };
 
-// Launch the fused kernel.  tile_tets selects the compiled variant.  Returns cudaError_t.
-cudaError_t launch_energy_grad(const KParams &p, int tile_tets, int n_vertices, const int32_t *slot_ptr, cudaStream_t stream);
-// One-time per-process attribute setup for a variant (dynamic smem opt-in).  Returns cudaError_t.
-cudaError_t prepare_energy_grad(int tile_tets);
-int nvmax_for(int tile_tets);     // staged-vertex capacity of the compiled variant (0 = not compiled)
+struct LaunchConfig {
+  int nw;          // warps per CTA (8 or 16)
+  int grid;        // persistent CTAs
+  int smem_bytes;  // dynamic shared memory
+  int global;      // GLOBAL mode
+};
 
-void set_threads_512(int nt);
-void set_skip_combine(int v);
-void set_pdl_tile(int v);
-void set_exp_flags(int v);
+// Dynamic shared memory the kernel needs for a configuration (ring_slots chunks of cells_per_chunk cells per warp).
+int energy_ring_bytes(int ring_slots, int cells_per_chunk, bool global);
+int energy_smem_bytes(int nw, int ring_slots, int cells_per_chunk, int area_verts, bool global);
+constexpr unsigned long long kEnergySentinel = 0x7FF8F00DBAADC0DEull;   // initial value of cta_energy
+// Max co-resident CTAs per SM for a configuration (0 if it does not fit); also opts in to the smem size.
+cudaError_t energy_occupancy(int nw, int smem_bytes, bool global, int *ctas_per_sm);
+cudaError_t launch_energy_grad(const KParams &p, const LaunchConfig &lc, cudaStream_t stream);
 
 cudaError_t launch_scale(const float *g, int64_t count, float gradH, const float *gradH_dev, float *out, cudaStream_t s);
-cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work2, cudaStream_t st);
+cudaError_t launch_grad_limit(float *g, int64_t count, float thr, float s, float *work4, cudaStream_t st);
 cudaError_t launch_adam_uniform(float *p, const float *grad, float *g1, float *g2, int64_t count, double lr,
-                                double b1, double b2, int step, double grad_limit, float *work2, cudaStream_t st);
+                                double b1, double b2, int step, double grad_limit, float *work4, cudaStream_t st);
 
 }  // namespace tsb

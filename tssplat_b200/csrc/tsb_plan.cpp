@@ -1,11 +1,16 @@
-// Host plan builder: rest inverses, face adjacency, locality-ordered tiles, per-tile vertex
-// staging lists, gather tables and the shared-vertex combine lists.  See tsb_plan.h.
+// Host plan builder: validation, face adjacency, connected components, the fp64 biharmonic operator
+// rows (M = G^T L^T L G, off-diagonal part), 1/det(Dm) per tet, cost-balanced segmentation over the
+// persistent CTAs and their warps, and the per-warp TMA byte streams.  See tsb_plan.h.
 #include "tsb_plan.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
+#include <thread>
 
 #include "../../include/tssplat_b200.h"
 
@@ -25,15 +30,6 @@ struct FaceKey {
 // Face k of a tet is the face opposite to local vertex k.
 const int kFace[4][3] = {{1, 2, 3}, {0, 3, 2}, {0, 1, 3}, {0, 2, 1}};
 
-inline uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
-  v &= 0x3ff;
-  v = (v | (v << 16)) & 0x030000FF;
-  v = (v | (v << 8)) & 0x0300F00F;
-  v = (v | (v << 4)) & 0x030C30C3;
-  v = (v | (v << 2)) & 0x09249249;
-  return v;
-}
-
 struct UnionFind {
   std::vector<int32_t> p;
   explicit UnionFind(int n) : p(n) { std::iota(p.begin(), p.end(), 0); }
@@ -47,7 +43,8 @@ struct UnionFind {
   }
 };
 
-bool invert3(const double *m, double *o) {
+// B = Dm^-1 (row-major) and det(Dm).  Returns false for a degenerate tet.
+bool invert3(const double *m, double *o, double *det) {
   const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
   const double d = m[0] * c00 + m[1] * c01 + m[2] * c02;
   if (d == 0.0 || !std::isfinite(d)) return false;
@@ -55,24 +52,451 @@ bool invert3(const double *m, double *o) {
   o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
   o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
   o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  *det = d;
   return true;
+}
+
+// One connected component: its vertices (sorted global ids), tets, and operator rows.
+struct Comp {
+  std::vector<int32_t> verts;   // sorted global ids; local id = position
+  std::vector<int32_t> tets;    // global tet ids, ascending
+  std::vector<int32_t> rptr;    // [nv+1]
+  std::vector<int32_t> col;     // local column ids (sorted inside a row), off-diagonal only
+  std::vector<float> val;
+  std::vector<int32_t> pos;     // staging position of each local vertex (bank-coloured); identity in GLOBAL mode
+  int32_t npos = 0;             // positions used (8 * largest colour class)
+  int32_t first_of_color[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // a vertex with each (position mod 8): wildcard padding targets
+  int32_t contiguous = 1;
+};
+
+struct Mesh {
+  const float *rest;
+  const int32_t *tets;
+  int32_t n, nele;
+  std::vector<int32_t> nbr;       // [4*nele] neighbour tet across face k, -1 = boundary
+  std::vector<int32_t> local_of;  // [n] local id of a vertex inside its component
+  int32_t lap_scale;
+};
+
+// Rows of M = G^T L^T L G for one component, in fp64, off-diagonal entries rounded to fp32.
+//   F_t = sum_v x_v (x) a_{t,v}  (a = rest gradients of the hat functions: rows of Dm^-1, geometry/mesh_utils.py:38-69)
+//   (L F)_t = w_t (deg_t F_t - sum_{s ~ t} F_s) = sum_v x_v (x) W_{t,v},   W_{t,v} = w_t (deg_t a_{t,v} - sum_s a_{s,v})
+//   M_ij = sum_t W_{t,i} . W_{t,j}          (per coordinate; the reference's matrix is M (x) I_3)
+// L is the face-adjacency graph Laplacian of the tets (THE libpgo assumption, oracle/tet_energy_oracle.py:
+// tet_laplacian), w_t = 1 (unscaled, what the reference requests) or 1/deg_t (laplacian_scale = 1).
+void build_rows(const Mesh &M, Comp &C) {
+  const int nv = int(C.verts.size()), nt = int(C.tets.size());
+  // hat gradients of every tet of the component (fp64)
+  std::vector<double> A(size_t(nt) * 12);
+  {
+    for (int tl = 0; tl < nt; ++tl) {
+      const int32_t *v = M.tets + 4 * size_t(C.tets[tl]);
+      double Dm[9], B[9], det;
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) Dm[3 * r + k] = double(M.rest[3 * size_t(v[k + 1]) + r]) - double(M.rest[3 * size_t(v[0]) + r]);
+      invert3(Dm, B, &det);   // validated earlier
+      double *a = &A[size_t(tl) * 12];
+      for (int c = 0; c < 3; ++c) {
+        a[3 + c] = B[c]; a[6 + c] = B[3 + c]; a[9 + c] = B[6 + c];
+        a[c] = -(B[c] + B[3 + c] + B[6 + c]);
+      }
+    }
+  }
+  // local tet lookup through a sorted search (component tets are ascending)
+  auto tl_find = [&](int32_t t) { return int(std::lower_bound(C.tets.begin(), C.tets.end(), t) - C.tets.begin()); };
+
+  // per-tet stencils: up to 8 (vertex, W) pairs
+  struct Ent { int32_t v; double w[3]; };
+  std::vector<Ent> st(size_t(nt) * 8);
+  std::vector<uint8_t> cnt(nt, 0);
+  std::vector<int32_t> inc_ptr(size_t(nv) + 1, 0);
+  for (int tl = 0; tl < nt; ++tl) {
+    const int32_t t = C.tets[tl];
+    Ent *e = &st[size_t(tl) * 8];
+    int ne = 0;
+    int deg = 0;
+    for (int k = 0; k < 4; ++k) deg += M.nbr[4 * size_t(t) + k] >= 0;
+    const double wt = M.lap_scale ? (deg > 0 ? 1.0 / deg : 0.0) : 1.0;
+    auto add = [&](int32_t vloc, const double *a, double coef) {
+      for (int i = 0; i < ne; ++i)
+        if (e[i].v == vloc) { for (int c = 0; c < 3; ++c) e[i].w[c] += coef * a[c]; return; }
+      e[ne].v = vloc;
+      for (int c = 0; c < 3; ++c) e[ne].w[c] = coef * a[c];
+      ++ne;
+    };
+    const int32_t *v = M.tets + 4 * size_t(t);
+    for (int k = 0; k < 4; ++k) add(M.local_of[v[k]], &A[size_t(tl) * 12 + 3 * k], wt * deg);
+    for (int f = 0; f < 4; ++f) {
+      const int32_t s = M.nbr[4 * size_t(t) + f];
+      if (s < 0) continue;
+      const int sl = tl_find(s);
+      const int32_t *vs = M.tets + 4 * size_t(s);
+      for (int k = 0; k < 4; ++k) add(M.local_of[vs[k]], &A[size_t(sl) * 12 + 3 * k], -wt);
+    }
+    cnt[tl] = uint8_t(ne);
+    for (int i = 0; i < ne; ++i) ++inc_ptr[e[i].v + 1];
+  }
+  for (int i = 0; i < nv; ++i) inc_ptr[i + 1] += inc_ptr[i];
+  std::vector<int32_t> inc(static_cast<size_t>(inc_ptr[nv]), 0);   // (tl * 8 + slot)
+  {
+    std::vector<int32_t> cur(inc_ptr.begin(), inc_ptr.end() - 1);
+    for (int tl = 0; tl < nt; ++tl)
+      for (int i = 0; i < cnt[tl]; ++i) inc[cur[st[size_t(tl) * 8 + i].v]++] = tl * 8 + i;
+  }
+  // rows
+  C.rptr.assign(size_t(nv) + 1, 0);
+  C.col.clear(); C.val.clear();
+  C.col.reserve(size_t(nv) * 40); C.val.reserve(size_t(nv) * 40);
+  std::vector<double> acc(nv, 0.0);
+  std::vector<uint8_t> seen(nv, 0);
+  std::vector<int32_t> touched;
+  for (int i = 0; i < nv; ++i) {
+    touched.clear();
+    for (int32_t p = inc_ptr[i]; p < inc_ptr[i + 1]; ++p) {
+      const int tl = inc[p] >> 3, si = inc[p] & 7;
+      const Ent *e = &st[size_t(tl) * 8];
+      const double *wi = e[si].w;
+      for (int j = 0; j < cnt[tl]; ++j) {
+        const int32_t vj = e[j].v;
+        if (vj == i) continue;
+        if (!seen[vj]) { seen[vj] = 1; touched.push_back(vj); }
+        acc[vj] += wi[0] * e[j].w[0] + wi[1] * e[j].w[1] + wi[2] * e[j].w[2];
+      }
+    }
+    std::sort(touched.begin(), touched.end());
+    for (int32_t vj : touched) {
+      C.col.push_back(vj);
+      C.val.push_back(float(acc[vj]));      // fp64 -> fp32 like the reference's operators (tet_spheres.cpp:43-45)
+      acc[vj] = 0.0; seen[vj] = 0;
+    }
+    C.rptr[i + 1] = int32_t(C.col.size());
+  }
+}
+
+// Bank-aware staging positions (see HostPlan::pos16).  Greedy balanced 8-colouring of the operator's
+// sparsity graph: a vertex takes the colour that is rarest among the columns of the rows it appears in
+// (the pattern is symmetric, so those rows are its own columns); position = 8 * (rank in colour) + colour.
+void place_vertices(Comp &C, bool identity) {
+  const int nv = int(C.verts.size());
+  C.pos.resize(nv);
+  if (identity || nv < 64) {
+    for (int v = 0; v < nv; ++v) C.pos[v] = v;
+    C.npos = nv;
+    for (int c = 0; c < 8; ++c) C.first_of_color[c] = c < nv ? c : 0;
+    return;
+  }
+  std::vector<int32_t> cnt(size_t(nv) * 8, 0);
+  std::vector<int32_t> order(nv), color(nv, -1);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return C.rptr[a + 1] - C.rptr[a] > C.rptr[b + 1] - C.rptr[b]; });
+  int glob[8] = {0};
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    for (int v : order) {
+      const int32_t *nb = &C.col[size_t(C.rptr[v])];
+      const int deg = C.rptr[v + 1] - C.rptr[v];
+      if (color[v] >= 0) {
+        for (int k = 0; k < deg; ++k) --cnt[size_t(nb[k]) * 8 + color[v]];
+        --glob[color[v]];
+      }
+      int64_t cost[8] = {0};
+      for (int k = 0; k < deg; ++k)
+        for (int c = 0; c < 8; ++c) cost[c] += cnt[size_t(nb[k]) * 8 + c];
+      int best = 0;
+      for (int c = 1; c < 8; ++c)
+        if (cost[c] * 1024 + glob[c] < cost[best] * 1024 + glob[best]) best = c;
+      color[v] = best;
+      for (int k = 0; k < deg; ++k) ++cnt[size_t(nb[k]) * 8 + best];
+      ++glob[best];
+    }
+  }
+  int rank[8] = {0};
+  for (int c = 0; c < 8; ++c) C.first_of_color[c] = -1;
+  for (int v = 0; v < nv; ++v) {
+    const int c = color[v];
+    C.pos[v] = 8 * rank[c]++ + c;
+    if (C.first_of_color[c] < 0) C.first_of_color[c] = v;
+  }
+  int mx = 0;
+  for (int c = 0; c < 8; ++c) { mx = std::max(mx, rank[c]); if (C.first_of_color[c] < 0) C.first_of_color[c] = 0; }
+  C.npos = 8 * mx;
+}
+
+template <class T>
+void put(std::vector<uint8_t> &b, size_t off, T v) { std::memcpy(b.data() + off, &v, sizeof(T)); }
+
+struct RowRef { int32_t row; int32_t len; };
+
+// quad cells an RB of these rows needs when each row is split over L lanes (slot 0 of a lane = header)
+inline int rb_len4(const RowRef *rows, int nrows, int L) {
+  int len4 = 1;
+  for (int i = 0; i < nrows; ++i) {
+    const int per_lane = (rows[i].len + L - 1) / L;       // lane 0 of the row holds the most
+    len4 = std::max(len4, (per_lane + 1 + 3) / 4);
+  }
+  return len4;
+}
+
+// Shared-memory bank model of the kernel's 128-bit gathers: a quarter-warp (8 adjacent lanes) is served
+// in one wavefront when its 8 float4 addresses fall into 8 different 16-byte bank groups, i.e. when the
+// vertex ids differ mod 8 (all lanes add the same base).  Within a row the order of the entries is free
+// and padding slots may point at ANY vertex (their weight is 0), so for every slot column we match the 8
+// lanes of a quarter to 8 distinct residues.  Returns the slot layout: slot_col[lane][slot] (local vertex
+// id, -1 = wildcard padding that still needs a residue) and slot_ent[lane][slot] (entry index or -1).
+struct LaneSlots {
+  std::vector<int32_t> col;   // [32 * nslots] local column id per (lane, slot)
+  std::vector<int32_t> ent;   // [32 * nslots] entry index inside the lane's row, -1 = padding
+};
+
+void assign_slots(const Comp &C, const RowRef *rows, int nrows, int L, int len4, LaneSlots &out) {
+  const int nslots = 4 * len4, NC = nslots - 1;       // colours = slots 1..nslots-1 (slot 0 is the header)
+  out.col.assign(size_t(32) * nslots, 0);
+  out.ent.assign(size_t(32) * nslots, -1);
+  int own[32];
+  for (int l = 0; l < 32; ++l) {
+    const int ri = l / L;
+    own[l] = ri < nrows ? rows[ri].row : 0;
+    out.col[size_t(l) * nslots] = own[l];             // slot 0 = header (own row)
+  }
+  // Per quarter-warp: proper edge colouring of the bipartite multigraph lanes x residues (one edge per
+  // operator entry, colour = slot).  Konig: possible with NC colours whenever no residue has more than NC
+  // entries among the quarter's 8 lanes; the few excess edges go to any free slot of their lane.
+  std::vector<int32_t> lane_ent(size_t(8) * NC), lane_res(size_t(8) * NC), res_lane(size_t(8) * NC);
+  std::vector<int32_t> overflow;
+  for (int q = 0; q < 4; ++q) {
+    std::fill(lane_ent.begin(), lane_ent.end(), -1);
+    std::fill(lane_res.begin(), lane_res.end(), -1);
+    std::fill(res_lane.begin(), res_lane.end(), -1);
+    int lane_deg[8] = {0}, res_deg[8] = {0};
+    auto L_ = [&](int i, int c) -> int32_t & { return lane_res[size_t(i) * NC + c]; };   // residue of lane i's edge coloured c
+    auto E_ = [&](int i, int c) -> int32_t & { return lane_ent[size_t(i) * NC + c]; };   // its entry index
+    auto R_ = [&](int r, int c) -> int32_t & { return res_lane[size_t(r) * NC + c]; };   // lane of residue r's edge coloured c
+    overflow.clear();
+    for (int i = 0; i < 8; ++i) {
+      const int l = 8 * q + i, ri = l / L, sub = l % L;
+      if (ri >= nrows) continue;
+      const int row = rows[ri].row, len = rows[ri].len;
+      const int32_t *col = &C.col[size_t(C.rptr[row])];
+      for (int e = sub; e < len; e += L) {
+        const int r = C.pos[col[e]] & 7;
+        if (res_deg[r] >= NC) { overflow.push_back(i * 65536 + e); continue; }   // residue saturated: unavoidable conflict
+        int a = 0, b = 0;
+        while (L_(i, a) >= 0) ++a;                     // free at the lane (lane degree <= NC by construction)
+        while (R_(r, b) >= 0) ++b;                     // free at the residue
+        if (R_(r, a) >= 0) {                           // a is taken at r: flip the a/b alternating path that starts at r
+          int rr = r, ca = a, cb = b;
+          // collect the path edges (lane, colour) then swap
+          int path_lane[64], path_col[64], np = 0;
+          int cur_r = rr;
+          bool at_res = true;
+          int cur_l = -1;
+          while (np < 64) {
+            if (at_res) {
+              const int ln = R_(cur_r, ca);
+              if (ln < 0) break;
+              path_lane[np] = ln; path_col[np] = ca; ++np;
+              cur_l = ln; at_res = false;
+            } else {
+              const int rn = L_(cur_l, cb);
+              if (rn < 0) break;
+              path_lane[np] = cur_l; path_col[np] = cb; ++np;
+              cur_r = rn; at_res = true;
+            }
+          }
+          // remove all path edges, then re-insert with swapped colours
+          int pe[64], pr[64];
+          for (int k = 0; k < np; ++k) {
+            const int ln = path_lane[k], c = path_col[k];
+            pe[k] = E_(ln, c); pr[k] = L_(ln, c);
+            R_(pr[k], c) = -1; L_(ln, c) = -1; E_(ln, c) = -1;
+          }
+          for (int k = 0; k < np; ++k) {
+            const int ln = path_lane[k], c = path_col[k] == ca ? cb : ca;
+            L_(ln, c) = pr[k]; E_(ln, c) = pe[k]; R_(pr[k], c) = ln;
+          }
+        }
+        L_(i, a) = r; E_(i, a) = e; R_(r, a) = i;
+        ++lane_deg[i]; ++res_deg[r];
+      }
+    }
+    for (int32_t oe : overflow) {                       // excess edges: any free slot of the lane
+      const int i = oe >> 16, e = oe & 0xFFFF;
+      int a = 0;
+      while (L_(i, a) >= 0) ++a;
+      L_(i, a) = 8;                                     // marks "placed, conflicts allowed"
+      E_(i, a) = e;
+    }
+    for (int c = 0; c < NC; ++c) {
+      uint32_t used = 0;
+      for (int i = 0; i < 8; ++i) if (L_(i, c) >= 0 && L_(i, c) < 8) used |= 1u << L_(i, c);
+      for (int i = 0; i < 8; ++i) {
+        const int l = 8 * q + i;
+        int32_t col_out;
+        if (E_(i, c) >= 0) {
+          col_out = C.col[size_t(C.rptr[own[l]]) + E_(i, c)];
+        } else {                                        // padding: any vertex with a residue nobody uses in this slot
+          int r = -1;
+          for (int k = 0; k < 8; ++k) if (!((used >> k) & 1u)) { r = k; break; }
+          if (r >= 0) { used |= 1u << r; col_out = C.first_of_color[r]; } else col_out = own[l];
+        }
+        out.col[size_t(l) * nslots + 1 + c] = col_out;
+        out.ent[size_t(l) * nslots + 1 + c] = E_(i, c);
+      }
+    }
+  }
+}
+
+// Appends one row block (len4 quad cells).  STAGED: IDX = uint16_t byte offsets into the staging area;
+// GLOBAL: IDX = uint32_t global ids (gid maps local -> global).  Returns len4.
+template <class IDX>
+int emit_rb(std::vector<uint8_t> &s, const Comp &C, const RowRef *rows, int nrows, int L, const int32_t *gid, int ubase_bytes,
+            LaneSlots &scratch, int64_t *conflict_stat) {
+  constexpr bool kGlobal = sizeof(IDX) == 4;
+  constexpr size_t CELL = kGlobal ? kCellGlobal : kCellStaged, WOFF = 128 * sizeof(IDX);
+  const int len4 = rb_len4(rows, nrows, L);
+  const int nslots = 4 * len4;
+  int llog = 0;
+  while ((1 << llog) < L) ++llog;
+  auto stored = [&](int32_t local) -> IDX { return kGlobal ? IDX(gid[local]) : IDX(ubase_bytes + C.pos[local] * 16); };
+  // Lane order inside the block is free: deal the rows to the four quarter-warps so that the header
+  // gathers (slot 0: every lane reads its own row) also hit distinct bank groups.
+  RowRef arranged[32];
+  if (L == 1 && !kGlobal) {
+    int fill[4] = {0, 0, 0, 0};
+    uint32_t qused[4] = {0, 0, 0, 0};
+    RowRef tmp[4][8];
+    std::vector<int> later;
+    for (int i = 0; i < nrows; ++i) {
+      const int r = C.pos[rows[i].row] & 7;
+      int best = -1;
+      for (int q = 0; q < 4; ++q)
+        if (fill[q] < 8 && !((qused[q] >> r) & 1u) && (best < 0 || fill[q] < fill[best])) best = q;
+      if (best < 0) { later.push_back(i); continue; }
+      tmp[best][fill[best]++] = rows[i];
+      qused[best] |= 1u << r;
+    }
+    for (int i : later) {
+      int best = 0;
+      for (int q = 1; q < 4; ++q) if (fill[q] < fill[best]) best = q;
+      tmp[best][fill[best]++] = rows[i];
+    }
+    // lanes of a quarter must be contiguous and idle lanes last: quarters are filled 0..3 in order of size
+    int order4[4] = {0, 1, 2, 3};
+    std::sort(order4, order4 + 4, [&](int a, int b) { return fill[a] > fill[b]; });
+    // idle lanes may only trail the active ones (rows[ri] with ri >= nrows is idle): compact quarter by quarter,
+    // keeping every full quarter intact
+    int n = 0;
+    for (int k = 0; k < 4; ++k)
+      for (int i = 0; i < fill[order4[k]]; ++i) arranged[n++] = tmp[order4[k]][i];
+    rows = arranged;
+  }
+  assign_slots(C, rows, nrows, L, len4, scratch);
+  size_t o = s.size();
+  s.resize(o + size_t(len4) * CELL, 0);
+  for (int l = 0; l < 32; ++l) {
+    const int ri = l / L;
+    const bool active = ri < nrows;
+    const int r = active ? rows[ri].row : 0;
+    const float *val = active ? &C.val[size_t(C.rptr[r])] : nullptr;
+    for (int slot = 0; slot < nslots; ++slot) {
+      const IDX id = stored(scratch.col[size_t(l) * nslots + slot]);
+      uint32_t wbits = 0;
+      if (slot == 0) {
+        // header: global row id (24 bits, 0xFFFFFF = idle lane) | len4 << 24 | log2(L) << 30.  Read as a float it
+        // is finite (len4 <= 62 keeps the exponent below 0xFF) and it multiplies a difference that is exactly 0.
+        const uint32_t rid = active ? uint32_t(kGlobal ? gid[r] : C.verts[r]) : 0xFFFFFFu;
+        wbits = rid | (uint32_t(len4) << 24) | (uint32_t(llog) << 30);
+      } else {
+        const int e = scratch.ent[size_t(l) * nslots + slot];
+        if (e >= 0) std::memcpy(&wbits, &val[e], 4);
+      }
+      const size_t cell = o + size_t(slot / 4) * CELL;
+      put<IDX>(s, cell + (size_t(l) * 4 + (slot & 3)) * sizeof(IDX), id);
+      put<uint32_t>(s, cell + WOFF + (size_t(l) * 4 + (slot & 3)) * 4, wbits);
+    }
+  }
+  if (conflict_stat) {      // wavefronts of the gathers: ideal = 1 per (quarter, slot)
+    for (int q = 0; q < 4; ++q)
+      for (int slot = 0; slot < nslots; ++slot) {
+        int cnt[8] = {0};
+        int32_t first[8];
+        for (int k = 0; k < 8; ++k) first[k] = -1;
+        int worst = 1;
+        for (int i = 0; i < 8; ++i) {
+          const int32_t c = C.pos[scratch.col[size_t(8 * q + i) * nslots + slot]];
+          const int r = c & 7;
+          if (first[r] == c) continue;              // same address: broadcast, no extra wavefront
+          if (first[r] < 0) first[r] = c;
+          ++cnt[r];
+          worst = std::max(worst, cnt[r]);
+        }
+        conflict_stat[0] += worst;
+        conflict_stat[1] += 1;
+      }
+  }
+  return len4;
+}
+
+// Appends one tet cell: STAGED 64 tets (2 per lane), GLOBAL 32 tets.
+template <class IDX>
+void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int nt, int xbase_bytes, int64_t *stat) {
+  constexpr bool kGlobal = sizeof(IDX) == 4;
+  constexpr size_t CELL = kGlobal ? kCellGlobal : kCellStaged;
+  constexpr int TPL = kGlobal ? 1 : 2;
+  constexpr size_t DOFF = 32 * TPL * 4 * sizeof(IDX);
+  size_t o = s.size();
+  s.resize(o + CELL, 0);
+  if (!kGlobal)   // padding tets: four times the component's vertex 0 (det 0) with 1/det(Dm) = 0
+    for (int i = 0; i < 32 * TPL * 4; ++i) put<IDX>(s, o + size_t(i) * sizeof(IDX), IDX(xbase_bytes + C.pos[0] * 16));
+  // The barrier is invariant under any relabelling of a tet's vertices as long as 1/det(Dm) is taken for
+  // the same order, so each tet's vertex order is chosen to give the 8 lanes of a quarter-warp distinct
+  // bank groups in each of its 4 gathers (greedy over the 24 permutations).
+  static const uint8_t kPerm[24][4] = {{0,1,2,3},{0,1,3,2},{0,2,1,3},{0,2,3,1},{0,3,1,2},{0,3,2,1},{1,0,2,3},{1,0,3,2},{1,2,0,3},{1,2,3,0},{1,3,0,2},{1,3,2,0},
+                                       {2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},{2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
+  uint32_t used[4][2][4];      // [quarter][tet slot][gather] -> residues taken
+  std::memset(used, 0, sizeof(used));
+  for (int i = 0; i < nt; ++i) {
+    const int l = i / TPL, k = i % TPL;          // lane, tet slot inside the lane
+    const int32_t t = C.tets[size_t(t0) + i];
+    const int32_t *v0 = M.tets + 4 * size_t(t);
+    int32_t v[4] = {v0[0], v0[1], v0[2], v0[3]};
+    if (!kGlobal) {
+      int res[4];
+      for (int c = 0; c < 4; ++c) res[c] = C.pos[M.local_of[v0[c]]] & 7;
+      uint32_t *u = used[l / 8][k];
+      int best = 0, best_hits = 99;
+      for (int pi = 0; pi < 24; ++pi) {
+        int hits = 0;
+        for (int c = 0; c < 4; ++c) hits += (u[c] >> res[kPerm[pi][c]]) & 1u;
+        if (hits < best_hits) { best_hits = hits; best = pi; if (!hits) break; }
+      }
+      for (int c = 0; c < 4; ++c) { v[c] = v0[kPerm[best][c]]; u[c] |= 1u << res[kPerm[best][c]]; }
+      if (stat) { stat[0] += best_hits; stat[1] += 4; }
+    }
+    double Dm[9], B[9], det;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Dm[3 * r + c] = double(M.rest[3 * size_t(v[c + 1]) + r]) - double(M.rest[3 * size_t(v[0]) + r]);
+    invert3(Dm, B, &det);
+    for (int c = 0; c < 4; ++c)
+      put<IDX>(s, o + ((size_t(l) * TPL + k) * 4 + c) * sizeof(IDX), kGlobal ? IDX(v[c]) : IDX(xbase_bytes + C.pos[M.local_of[v[c]]] * 16));
+    if (!kGlobal && std::getenv("TSB_EXPERIMENT_NOCONFLICT"))
+      for (int c = 0; c < 4; ++c) put<IDX>(s, o + ((size_t(l) * TPL + k) * 4 + c) * sizeof(IDX), IDX(xbase_bytes + (l & 7) * 16));
+    put<float>(s, o + DOFF + (size_t(l) * TPL + k) * 4, float(1.0 / det));
+  }
 }
 
 }  // namespace
 
-int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, const PlanOptions &opt,
+int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, const PlanConfig &cfg,
                HostPlan &P, std::string &err) {
   if (!rest || !tets || n <= 0 || nele <= 0) { err = "null input or non-positive size"; return TSB_E_INVALID; }
-  const int TT = opt.tile_tets, NVMAX = opt.max_local_vertices;
-  if (TT < 32 || TT > 2048 || (TT % 32) != 0 || NVMAX < 32 || NVMAX > 0x7FFF || (NVMAX % 32) != 0) {
-    err = "tile_tets must be a multiple of 32 in [32,2048]";
-    return TSB_E_INVALID;
-  }
+  if (cfg.nw < 1 || cfg.nw > kMaxWarps || cfg.grid < 1) { err = "bad plan configuration"; return TSB_E_INVALID; }
+  if (n >= 0xFFFFFF) { err = "more than 16.7 M vertices in one handle (row-block headers hold 24-bit row ids): shard the mesh"; return TSB_E_INVALID; }
   P = HostPlan();
-  P.n = n; P.nele = nele; P.tile_tets = TT; P.max_local_vertices = NVMAX; P.laplacian_scale = opt.laplacian_scale;
+  P.n = n; P.nele = nele; P.laplacian_scale = cfg.laplacian_scale ? 1 : 0;
+  P.nw = cfg.nw;
+  const int NW = cfg.nw;
 
-  // ---- validate, rest inverses (fp64 -> fp32 like the reference: tet_spheres.cpp:43-45) --------
-  std::vector<float> Binv(size_t(nele) * 9);
+  // ---- validate ----------------------------------------------------------------------------------
   for (int t = 0; t < nele; ++t) {
     const int32_t *v = tets + 4 * size_t(t);
     for (int k = 0; k < 4; ++k)
@@ -80,21 +504,24 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     if (v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3]) {
       err = "tet " + std::to_string(t) + " repeats a vertex"; return TSB_E_MESH;
     }
-    double Dm[9], Bi[9];
+    double Dm[9], Bi[9], det;
     for (int r = 0; r < 3; ++r)
       for (int k = 0; k < 3; ++k) Dm[3 * r + k] = double(rest[3 * size_t(v[k + 1]) + r]) - double(rest[3 * size_t(v[0]) + r]);
-    if (!invert3(Dm, Bi)) { err = "tet " + std::to_string(t) + " has zero rest volume"; return TSB_E_MESH; }
-    for (int i = 0; i < 9; ++i) Binv[size_t(t) * 9 + i] = float(Bi[i]);
+    if (!invert3(Dm, Bi, &det) || !std::isfinite(float(1.0 / det))) {
+      err = "tet " + std::to_string(t) + " has zero rest volume"; return TSB_E_MESH;
+    }
   }
 
-  // ---- face adjacency -> opposite vertex across each face ---------------------------------------
-  std::vector<int32_t> opp(size_t(nele) * 4, -1);  // global id of the neighbour's vertex not on the shared face
+  // ---- face adjacency (neighbour tet across each face) and vertex components -----------------------
+  Mesh M{rest, tets, n, nele, std::vector<int32_t>(size_t(nele) * 4, -1), std::vector<int32_t>(size_t(n), -1), P.laplacian_scale};
   UnionFind uf(n);
+  std::vector<uint8_t> used(n, 0);
   {
     std::vector<FaceKey> fk(size_t(nele) * 4);
     for (int t = 0; t < nele; ++t) {
       const int32_t *v = tets + 4 * size_t(t);
       uf.unite(v[0], v[1]); uf.unite(v[0], v[2]); uf.unite(v[0], v[3]);
+      used[v[0]] = used[v[1]] = used[v[2]] = used[v[3]] = 1;
       for (int k = 0; k < 4; ++k) {
         uint32_t f[3] = {uint32_t(v[kFace[k][0]]), uint32_t(v[kFace[k][1]]), uint32_t(v[kFace[k][2]])};
         if (f[0] > f[1]) std::swap(f[0], f[1]);
@@ -111,329 +538,271 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       if (j - i > 2) { err = "non-manifold mesh: a face is shared by more than two tets"; return TSB_E_MESH; }
       if (j - i == 2) {
         const uint32_t o0 = fk[i].owner, o1 = fk[i + 1].owner;
-        opp[o0] = tets[o1];  // tets[4*t1 + k1] is the vertex of t1 opposite the shared face
-        opp[o1] = tets[o0];
+        M.nbr[o0] = int32_t(o1 >> 2);
+        M.nbr[o1] = int32_t(o0 >> 2);
       } else {
         ++P.n_boundary_faces;
       }
       i = j;
     }
   }
-
-  // ---- locality order: (component, Morton code of the rest centroid inside the component bbox) --
-  std::vector<int32_t> comp_of_vertex(n);
+  std::vector<Comp> comps;
   {
     std::vector<int32_t> label(n, -1);
-    int32_t nc = 0;
     for (int v = 0; v < n; ++v) {
+      if (!used[v]) { P.orphans.push_back(v); continue; }
       const int r = uf.find(v);
-      if (label[r] < 0) label[r] = nc++;
-      comp_of_vertex[v] = label[r];
+      if (label[r] < 0) { label[r] = int32_t(comps.size()); comps.emplace_back(); }
+      Comp &C = comps[label[r]];
+      M.local_of[v] = int32_t(C.verts.size());
+      C.verts.push_back(v);
     }
-    P.n_components = nc;
-  }
-  const int NC = P.n_components;
-  std::vector<float> lo(size_t(NC) * 3, 3.0e38f), hi(size_t(NC) * 3, -3.0e38f);
-  for (int v = 0; v < n; ++v) {
-    const int c = comp_of_vertex[v];
-    for (int r = 0; r < 3; ++r) {
-      lo[3 * size_t(c) + r] = std::min(lo[3 * size_t(c) + r], rest[3 * size_t(v) + r]);
-      hi[3 * size_t(c) + r] = std::max(hi[3 * size_t(c) + r], rest[3 * size_t(v) + r]);
+    for (int t = 0; t < nele; ++t) comps[label[uf.find(tets[4 * size_t(t)])]].tets.push_back(t);
+    for (Comp &C : comps) {
+      for (size_t k = 0; k < C.verts.size(); ++k)
+        if (C.verts[k] != C.verts[0] + int32_t(k)) { C.contiguous = 0; break; }
+      P.max_comp_verts = std::max<int32_t>(P.max_comp_verts, int32_t(C.verts.size()));
+      if (!C.contiguous) P.contiguous = 0;
     }
   }
-  std::vector<uint64_t> key(nele);
-  for (int t = 0; t < nele; ++t) {
-    const int32_t *v = tets + 4 * size_t(t);
-    const int c = comp_of_vertex[v[0]];
-    uint32_t q[3];
-    for (int r = 0; r < 3; ++r) {
-      const float cen = 0.25f * (rest[3 * size_t(v[0]) + r] + rest[3 * size_t(v[1]) + r] + rest[3 * size_t(v[2]) + r] + rest[3 * size_t(v[3]) + r]);
-      const float ext = hi[3 * size_t(c) + r] - lo[3 * size_t(c) + r];
-      float u = ext > 0.f ? (cen - lo[3 * size_t(c) + r]) / ext : 0.f;
-      u = std::min(std::max(u, 0.f), 1.f);
-      q[r] = uint32_t(u * 1023.f);
-    }
-    const uint32_t m = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
-    key[t] = (uint64_t(uint32_t(c)) << 32) | m;
-  }
-  P.tet_order.resize(nele);
-  std::iota(P.tet_order.begin(), P.tet_order.end(), 0);
-  std::stable_sort(P.tet_order.begin(), P.tet_order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
-
-  // ---- tiling: recursive coordinate bisection inside each component ----------------------------
-  // The tile count is matched to the SM count (a whole number of waves), tiles are distributed over
-  // components in proportion to their tet counts, and each component is split into boxy parts of
-  // (almost) equal size; inside a tile tets keep the Morton order (locality of the warp's gathers).
-  // A tile that would stage more than NVMAX vertices makes its component use one more tile.
+  const int NC = int(comps.size());
+  P.n_components = NC;
+  // ---- operator rows, component-parallel ------------------------------------------------------------
   {
-    // component -> [begin, end) in tet_order (tet_order is sorted by component first)
-    std::vector<int32_t> comp_begin(size_t(NC) + 1, 0);
-    for (int t = 0; t < nele; ++t) comp_begin[size_t(key[t] >> 32) + 1]++;
-    for (int c = 0; c < NC; ++c) comp_begin[size_t(c) + 1] += comp_begin[c];
-    int64_t target = (int64_t(nele) + TT - 1) / TT;
-    if (opt.balance_sms > 0) {
-      const int64_t per_round = int64_t(opt.balance_sms) * TT;
-      const int64_t rounds = (int64_t(nele) + per_round - 1) / per_round;
-      // do not go below a quarter-full tile: tiny meshes keep a handful of tiles
-      target = std::min<int64_t>(rounds * opt.balance_sms, std::max<int64_t>(target, (int64_t(nele) + TT / 4 - 1) / (TT / 4)));
-    }
-    std::vector<float> cen(size_t(nele) * 3);
-    for (int t = 0; t < nele; ++t) {
-      const int32_t *v = tets + 4 * size_t(t);
-      for (int r = 0; r < 3; ++r)
-        cen[3 * size_t(t) + r] = 0.25f * (rest[3 * size_t(v[0]) + r] + rest[3 * size_t(v[1]) + r] + rest[3 * size_t(v[2]) + r] + rest[3 * size_t(v[3]) + r]);
-    }
-    std::vector<int32_t> stamp(n, -1);
-    int stamp_id = 0;
-    auto staged_vertices = [&](const int32_t *first, const int32_t *last) {
-      ++stamp_id;
-      int cnt = 0;
-      for (const int32_t *it = first; it != last; ++it)
-        for (int k = 0; k < 4; ++k) {
-          const int32_t a0 = tets[4 * size_t(*it) + k], a1 = opp[4 * size_t(*it) + k];
-          if (stamp[a0] != stamp_id) { stamp[a0] = stamp_id; ++cnt; }
-          if (a1 >= 0 && stamp[a1] != stamp_id) { stamp[a1] = stamp_id; ++cnt; }
-        }
-      return cnt;
+    int nth = cfg.threads > 0 ? cfg.threads : int(std::thread::hardware_concurrency());
+    nth = std::max(1, std::min({nth, 32, NC}));
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int c = next.fetch_add(1); c < NC; c = next.fetch_add(1)) build_rows(M, comps[c]);
     };
-    std::vector<int32_t> work;          // tets of one component, permuted in place by the bisection
-    std::vector<std::pair<int32_t, int32_t>> parts;   // [begin,end) in `work`
-    struct Job { int32_t b, e, k; };
-    std::vector<Job> stack;
-    std::vector<int32_t> new_order;
-    new_order.reserve(nele);
-    P.tile_first.clear();
-    int max_fill = 0;
-    for (int c = 0; c < NC; ++c) {
-      const int cb = comp_begin[c], ce = comp_begin[size_t(c) + 1], nt = ce - cb;
-      int k = int(std::max<int64_t>((nt + TT - 1) / TT, (int64_t(nt) * target + nele / 2) / nele));
-      k = std::max(1, std::min(k, nt));
-      for (;;) {
-        work.assign(P.tet_order.begin() + cb, P.tet_order.begin() + ce);
-        parts.clear();
-        stack.clear();
-        stack.push_back(Job{0, nt, k});
-        while (!stack.empty()) {
-          const Job j = stack.back();
-          stack.pop_back();
-          if (j.k == 1) { parts.emplace_back(j.b, j.e); continue; }
-          float lo3[3] = {3e38f, 3e38f, 3e38f}, hi3[3] = {-3e38f, -3e38f, -3e38f};
-          for (int i = j.b; i < j.e; ++i)
-            for (int r = 0; r < 3; ++r) {
-              lo3[r] = std::min(lo3[r], cen[3 * size_t(work[i]) + r]);
-              hi3[r] = std::max(hi3[r], cen[3 * size_t(work[i]) + r]);
-            }
-          int ax = 0;
-          for (int r = 1; r < 3; ++r) if (hi3[r] - lo3[r] > hi3[ax] - lo3[ax]) ax = r;
-          const int k1 = j.k / 2, k2 = j.k - k1;
-          const int n1 = int((int64_t(j.e - j.b) * k1 + j.k / 2) / j.k);
-          std::nth_element(work.begin() + j.b, work.begin() + j.b + n1, work.begin() + j.e, [&](int32_t a, int32_t b2) {
-            const float ca = cen[3 * size_t(a) + ax], cb2 = cen[3 * size_t(b2) + ax];
-            return ca < cb2 || (ca == cb2 && a < b2);
-          });
-          stack.push_back(Job{j.b + n1, j.e, k2});
-          stack.push_back(Job{j.b, j.b + n1, k1});
-        }
-        bool ok = true;
-        for (const auto &pr : parts) {
-          if (pr.second - pr.first > TT) { ok = false; break; }
-          if (staged_vertices(work.data() + pr.first, work.data() + pr.second) > NVMAX) { ok = false; break; }
-        }
-        if (ok || k >= nt) break;
-        k = std::min(nt, k + std::max(1, k / 8));
-      }
-      std::sort(parts.begin(), parts.end());
-      for (const auto &pr : parts) {
-        if (pr.second == pr.first) continue;
-        std::sort(work.begin() + pr.first, work.begin() + pr.second, [&](int32_t a, int32_t b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
-        P.tile_first.push_back(int32_t(new_order.size()));
-        new_order.insert(new_order.end(), work.begin() + pr.first, work.begin() + pr.second);
-        max_fill = std::max(max_fill, pr.second - pr.first);
-      }
-    }
-    P.tile_first.push_back(nele);
-    P.tet_order.swap(new_order);
-    P.fill = std::min(TT, ((max_fill + 7) / 8) * 8);
-  }
-  const int NTILE = int(P.tile_first.size()) - 1;
-  P.n_tiles = NTILE;
-  const int64_t VB = vblob_bytes(TT, NVMAX), TB = tblob_bytes(TT);
-  const int NR = rows_cap(TT, NVMAX);
-  P.vblob.assign(size_t(NTILE) * VB, 0);
-  P.tblob.assign(size_t(NTILE) * TB, 0);
-
-  // ---- per tile: staged vertex list (id-sorted), local stencil ids, rest inverses ---------------
-  std::vector<int32_t> local_of(n, -1);
-  std::vector<std::vector<int32_t>> tile_verts(NTILE);
-  std::vector<uint16_t> idx8(size_t(NTILE) * TT * 8, 0);   // kept for the gather-table pass below
-  for (int tile = 0; tile < NTILE; ++tile) {
-    const int p0 = P.tile_first[tile], p1 = P.tile_first[tile + 1];
-    std::vector<int32_t> &vs = tile_verts[tile];
-    vs.reserve(size_t(p1 - p0));
-    for (int pos = p0; pos < p1; ++pos) {
-      const int t = P.tet_order[pos];
-      for (int k = 0; k < 4; ++k) {
-        vs.push_back(tets[4 * size_t(t) + k]);
-        if (opp[4 * size_t(t) + k] >= 0) vs.push_back(opp[4 * size_t(t) + k]);
-      }
-    }
-    std::sort(vs.begin(), vs.end());
-    vs.erase(std::unique(vs.begin(), vs.end()), vs.end());
-    for (size_t i = 0; i < vs.size(); ++i) local_of[vs[i]] = int32_t(i);
-    P.n_local_vertices += int64_t(vs.size());
-    uint8_t *tb = P.tblob.data() + size_t(tile) * TB;
-    uint16_t *ids = reinterpret_cast<uint16_t *>(tb);
-    float *Bt = reinterpret_cast<float *>(tb + size_t(16) * TT);
-    for (int pos = p0; pos < p1; ++pos) {
-      const int t = P.tet_order[pos], lt = pos - p0;
-      uint16_t *d = ids + size_t(lt) * 8, *d2 = &idx8[(size_t(tile) * TT + lt) * 8];
-      for (int k = 0; k < 4; ++k) {
-        d[k] = uint16_t(local_of[tets[4 * size_t(t) + k]]);
-        const int32_t o = opp[4 * size_t(t) + k];
-        // boundary face: point at the tet's own opposite vertex (harmless gather), bit 15 clear;
-        // interior face: neighbour's opposite vertex, bit 15 set
-        d[4 + k] = o >= 0 ? uint16_t(0x8000u | uint16_t(local_of[o])) : d[k];
-        d2[k] = d[k];
-        d2[4 + k] = o >= 0 ? uint16_t(local_of[o]) : uint16_t(0xFFFF);
-      }
-      for (int i = 0; i < 9; ++i) Bt[size_t(lt) * 9 + i] = Binv[size_t(t) * 9 + i];
+    if (nth == 1) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int i = 0; i < nth; ++i) th.emplace_back(work);
+      for (auto &t : th) t.join();
     }
   }
 
-  // ---- in-tile degree of every staged vertex -> gather-table rows -> scratch slots ----------------
-  // rows_of[tile][i] = ceil(deg / kRowCap) for the i-th staged vertex (id-sorted)
-  std::vector<std::vector<int32_t>> tile_deg(NTILE);
-  for (int tile = 0; tile < NTILE; ++tile) {
-    const int nv = int(tile_verts[tile].size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
-    std::vector<int32_t> &dg = tile_deg[tile];
-    dg.assign(nv, 0);
-    for (int lt = 0; lt < ntet; ++lt) {
-      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
-      for (int s = 0; s < 8; ++s) if (d[s] != 0xFFFF) dg[d[s]]++;
+  // ---- mode, bank-aware staging positions, staging capacities, grid ------------------------------------
+  bool global_mode = cfg.force_global || P.max_comp_verts > cfg.area_cap || P.max_comp_verts > kMaxStagedVerts;
+  auto place_all = [&](bool identity) {
+    int vh = 0, mx = 0;
+    for (Comp &C : comps) {
+      place_vertices(C, identity);
+      mx = std::max(mx, C.npos);
+      if (C.npos <= cfg.vh_cap) vh = std::max(vh, C.npos);
     }
+    P.vh = vh;
+    P.area_verts = std::max(2 * vh, mx);
+    return mx;
+  };
+  if (!global_mode) {
+    const int mx = place_all(std::getenv("TSSPLAT_B200_NO_PLACEMENT") != nullptr);
+    if (mx > cfg.area_cap || mx > kMaxStagedVerts) global_mode = true;     // colouring padded a borderline component over the cap
   }
-  // slot_ptr[v]..slot_ptr[v+1]: scratch slots of vertex v, ordered by (tile, row)
-  P.slot_ptr.assign(size_t(n) + 1, 0);
-  std::vector<int32_t> touches(n, 0);
-  for (int tile = 0; tile < NTILE; ++tile) {
-    const std::vector<int32_t> &vs = tile_verts[tile];
-    for (size_t i = 0; i < vs.size(); ++i) {
-      P.slot_ptr[size_t(vs[i]) + 1] += (tile_deg[tile][i] + kRowCap - 1) / kRowCap;
-      touches[vs[i]]++;
-    }
-  }
-  for (int v = 0; v < n; ++v) {
-    P.slot_ptr[size_t(v) + 1] += P.slot_ptr[v];
-    P.n_shared_vertices += touches[v] > 1;
-  }
-  if (int64_t(P.slot_ptr[n]) > int64_t(0x7fffffff) / 4) { err = "too many scratch slots"; return TSB_E_INVALID; }
-  P.n_slots = P.slot_ptr[n];
-  std::vector<int32_t> next_slot(P.slot_ptr.begin(), P.slot_ptr.end() - 1);   // tiles visited in ascending order
+  int G = cfg.grid;
+  if (cfg.grid_cb) G = cfg.grid_cb(P.vh, P.area_verts, global_mode);   // the caller sizes shared memory / occupancy
+  if (G < 1) { err = "bad grid size"; return TSB_E_INVALID; }
+  P.grid = G;
+  P.mode_global = global_mode ? 1 : 0;
+  const bool GLOBAL = global_mode;
+  if (GLOBAL) { place_all(true); P.vh = 0; P.area_verts = 0; }
 
-  // ---- per tile: vertex blob, gather table ---------------------------------------------------------
-  const int TTP = TT + 4;   // output-table row stride; column TT is the zero column
-  struct Row { int32_t vert, chunk, len; };
-  std::vector<Row> rows;
-  std::vector<int32_t> grp_rel, fill_cnt, row_n;
-  std::vector<uint16_t> row_ent;
-  for (int tile = 0; tile < NTILE; ++tile) {
-    const std::vector<int32_t> &vs = tile_verts[tile];
-    const std::vector<int32_t> &dg = tile_deg[tile];
-    const int nv = int(vs.size()), ntet = P.tile_first[tile + 1] - P.tile_first[tile];
-    uint8_t *vb = P.vblob.data() + size_t(tile) * VB;
-    TileHeader *hd = reinterpret_cast<TileHeader *>(vb);
-    int32_t *vlist = reinterpret_cast<int32_t *>(vb + 64);
-    float *Xx = reinterpret_cast<float *>(vb + 64 + size_t(4) * NVMAX);
-    float *YZ = reinterpret_cast<float *>(vb + 64 + size_t(8) * NVMAX);
-    int32_t *slot = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX);
-    int32_t *grp_ptr = reinterpret_cast<int32_t *>(vb + 64 + size_t(16) * NVMAX + size_t(4) * NR);
-    for (int i = 0; i < nv; ++i) {
-      vlist[i] = vs[i];
-      Xx[i] = rest[3 * size_t(vs[i])];
-      YZ[2 * i] = rest[3 * size_t(vs[i]) + 1];
-      YZ[2 * i + 1] = rest[3 * size_t(vs[i]) + 2];
+  // ---- cost stream and its G cuts --------------------------------------------------------------------
+  const double CR = 2.0, CT = double(cfg.tet_cost);
+  std::vector<double> crow(NC), ctot(NC), cbase(size_t(NC) + 1, 0.0);
+  for (int c = 0; c < NC; ++c) {
+    const Comp &C = comps[c];
+    crow[c] = double(C.col.size()) + CR * double(C.verts.size());
+    ctot[c] = crow[c] + CT * double(C.tets.size());
+    cbase[c + 1] = cbase[c] + ctot[c];
+    P.nnz += int64_t(C.col.size());
+  }
+  const double W = cbase[NC];
+  // cut b (1..G-1) -> (component, fraction), snapped to the component boundary when it would leave a sliver
+  struct Cut { int comp; double f; };
+  std::vector<Cut> cuts(size_t(G) + 1);
+  cuts[0] = {0, 0.0};
+  cuts[G] = {NC - 1, 1.0};
+  {
+    int c = 0;
+    for (int b = 1; b < G; ++b) {
+      const double p = W * double(b) / double(G);
+      while (c + 1 < NC && cbase[c + 1] <= p) ++c;
+      double f = ctot[c] > 0 ? (p - cbase[c]) / ctot[c] : 0.0;
+      const double eps = std::min(0.05, 0.15 * (W / G) / std::max(ctot[c], 1e-30));
+      if (f < eps) f = 0.0;
+      if (f > 1.0 - eps) f = 1.0;
+      cuts[b] = {c, f};
     }
-    // rows, longest first (stable: vertex id, then chunk)
-    rows.clear();
-    for (int i = 0; i < nv; ++i) {
-      const int nr = (dg[i] + kRowCap - 1) / kRowCap;
-      for (int c = 0; c < nr; ++c) rows.push_back(Row{i, c, std::min(kRowCap, dg[i] - c * kRowCap)});
+    for (int b = 1; b <= G; ++b) {   // monotone
+      const Cut &a = cuts[b - 1];
+      Cut &d = cuts[b];
+      if (d.comp < a.comp || (d.comp == a.comp && d.f < a.f)) d = a;
     }
-    std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.len > b.len; });
-    const int nrow = int(rows.size());
-    if (nrow > NR) { err = "internal: gather-table rows exceed capacity"; return TSB_E_INVALID; }
-    const int ngrp = (nrow + 31) / 32;
-    grp_rel.assign(size_t(ngrp) + 1, 0);
-    for (int g = 0; g < ngrp; ++g) grp_rel[g + 1] = grp_rel[g] + 32 * ((rows[size_t(g) * 32].len + 1) & ~1);
-    const int nell = ((grp_rel[ngrp] + 7) / 8) * 8;
-    if (nell > ell_cap(TT, NVMAX)) { err = "internal: gather table exceeds capacity"; return TSB_E_INVALID; }
-    while (P.ell.size() % 8) P.ell.push_back(uint16_t(TT));
-    if (P.ell.size() + size_t(nell) > size_t(0x7fffffff)) { err = "gather table exceeds 32-bit offsets"; return TSB_E_INVALID; }
-    hd->ntet = ntet; hd->nvert = nv; hd->nrow = nrow; hd->ell_off = int32_t(P.ell.size()); hd->nell = nell;
-    P.tile_ell.push_back(hd->ell_off); P.tile_ell.push_back(nell);
-    for (int g = 0; g <= ngrp; ++g) grp_ptr[g] = grp_rel[g];
-    P.ell.resize(size_t(hd->ell_off) + size_t(nell), uint16_t(TT));
-    // row index of (vertex, chunk 0); chunks of a vertex are NOT adjacent after sorting, so map each
-    std::vector<std::vector<int32_t>> row_of(nv);
-    for (int r = 0; r < nrow; ++r) {
-      std::vector<int32_t> &ro = row_of[rows[r].vert];
-      if (int(ro.size()) <= rows[r].chunk) ro.resize(size_t(rows[r].chunk) + 1, -1);
-      ro[rows[r].chunk] = r;
+  }
+
+  // ---- segments --------------------------------------------------------------------------------------
+  struct Seg { int comp; int r0, r1, t0, t1; };
+  std::vector<Seg> segs;
+  P.cta_seg.assign(size_t(G) * 2, 0);
+  std::vector<std::vector<double>> rowcum(NC);
+  auto row_at = [&](int c, double f) -> int {
+    const Comp &C = comps[c];
+    const int nv = int(C.verts.size());
+    if (f <= 0.0) return 0;
+    if (f >= 1.0) return nv;
+    std::vector<double> &rc = rowcum[c];
+    if (rc.empty()) {
+      rc.resize(size_t(nv) + 1, 0.0);
+      for (int i = 0; i < nv; ++i) rc[i + 1] = rc[i] + double(C.rptr[i + 1] - C.rptr[i]) + CR;
     }
-    // collect each row's entries (word offset of component 0 in the [24][TTP] table)
-    row_ent.assign(size_t(nrow) * kRowCap, 0);
-    row_n.assign(nrow, 0);
-    fill_cnt.assign(nv, 0);
-    for (int lt = 0; lt < ntet; ++lt) {
-      const uint16_t *d = &idx8[(size_t(tile) * TT + lt) * 8];
-      for (int s = 0; s < 8; ++s) {
-        if (d[s] == 0xFFFF) continue;
-        const int cnt = fill_cnt[d[s]]++;
-        const int r = row_of[d[s]][cnt / kRowCap];
-        row_ent[size_t(r) * kRowCap + row_n[r]++] = uint16_t(s * 3 * TTP + lt);
+    return int(std::lower_bound(rc.begin(), rc.end(), f * rc[nv]) - rc.begin());
+  };
+  auto tet_at = [&](int c, double f) -> int {
+    const int nt = int(comps[c].tets.size());
+    if (f <= 0.0) return 0;
+    if (f >= 1.0) return nt;
+    return int(std::llround(f * nt));
+  };
+  std::vector<int32_t> nseg_of(NC, 0);
+  for (int b = 0; b < G; ++b) {
+    P.cta_seg[2 * size_t(b)] = int32_t(segs.size());
+    const Cut lo = cuts[b], hi = cuts[b + 1];
+    for (int c = lo.comp; c <= hi.comp; ++c) {
+      const double f0 = (c == lo.comp) ? lo.f : 0.0, f1 = (c == hi.comp) ? hi.f : 1.0;
+      if (f1 <= f0) continue;
+      Seg s{c, row_at(c, f0), row_at(c, f1), tet_at(c, f0), tet_at(c, f1)};
+      if (s.r1 <= s.r0 && s.t1 <= s.t0) continue;
+      segs.push_back(s);
+      ++nseg_of[c];
+    }
+    P.cta_seg[2 * size_t(b) + 1] = int32_t(segs.size());
+  }
+  const int NS = int(segs.size());
+
+  // ---- staging tables ----------------------------------------------------------------------------------
+  std::vector<int32_t> x4off(size_t(NC) + 1, 0), p4off(size_t(NC) + 1, 0);
+  if (!GLOBAL) {
+    for (int c = 0; c < NC; ++c) x4off[c + 1] = x4off[c] + int32_t(comps[c].verts.size());
+    P.X4.assign(size_t(x4off[NC]) * 4, 0.f);
+    P.vlist.assign(size_t(x4off[NC]), 0);
+    P.pos16.assign(size_t(x4off[NC]), 0);
+    for (int c = 0; c < NC; ++c) p4off[c + 1] = p4off[c] + comps[c].npos;
+    P.pos_gid.assign(size_t(p4off[NC]), -1);
+    for (int c = 0; c < NC; ++c)
+      for (size_t k = 0; k < comps[c].verts.size(); ++k) {
+        const int32_t v = comps[c].verts[k];
+        for (int r = 0; r < 3; ++r) P.X4[(size_t(x4off[c]) + k) * 4 + r] = rest[3 * size_t(v) + r];
+        P.vlist[size_t(x4off[c]) + k] = v;
+        P.pos16[size_t(x4off[c]) + k] = uint16_t(comps[c].pos[k]);
+        P.pos_gid[size_t(p4off[c]) + comps[c].pos[k]] = v;
       }
-    }
-    // Order the entries of the 32 rows of a group so that, column by column, the 32 lanes of the
-    // warp read distinct shared-memory banks (bank = word offset mod 32; the three components
-    // are +TTP words apart, i.e. the same permutation shifted).  Greedy column-by-column
-    // matching, rows with the fewest remaining entries first within a column.
-    for (int g = 0; g < ngrp; ++g) {
-      const int r0 = g * 32, r1 = std::min(nrow, r0 + 32);
-      const int glen = (grp_rel[g + 1] - grp_rel[g]) / 32;
-      const size_t base = size_t(hd->ell_off) + size_t(grp_rel[g]);
-      uint8_t used_e[32][kRowCap] = {};
-      for (int k = 0; k < glen; ++k) {
-        uint32_t bank_used = 0;
-        // two passes: first place rows that can take a free bank, then the rest
-        int pending[32], np = 0;
-        for (int r = r0; r < r1; ++r) {
-          if (k >= row_n[r]) continue;   // this row is already exhausted -> padding (zero column)
-          int pick = -1;
-          for (int e = 0; e < row_n[r]; ++e) {
-            if (used_e[r - r0][e]) continue;
-            const int bank = row_ent[size_t(r) * kRowCap + e] & 31;
-            if (!(bank_used >> bank & 1u)) { pick = e; break; }
-          }
-          if (pick < 0) { pending[np++] = r; continue; }
-          used_e[r - r0][pick] = 1;
-          bank_used |= 1u << (row_ent[size_t(r) * kRowCap + pick] & 31);
-          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
-        }
-        for (int q = 0; q < np; ++q) {
-          const int r = pending[q];
-          int pick = -1;
-          for (int e = 0; e < row_n[r] && pick < 0; ++e) if (!used_e[r - r0][e]) pick = e;
-          used_e[r - r0][pick] = 1;
-          P.ell[base + size_t(k >> 1) * 64 + size_t(r - r0) * 2 + (k & 1)] = row_ent[size_t(r) * kRowCap + pick];
-        }
+  } else {
+    P.X4.assign(size_t(n) * 4, 0.f);
+    for (int v = 0; v < n; ++v)
+      for (int r = 0; r < 3; ++r) P.X4[size_t(v) * 4 + r] = rest[3 * size_t(v) + r];
+  }
+  P.segs.resize(NS);
+  for (int s = 0; s < NS; ++s) {
+    const Seg &g = segs[s];
+    const Comp &C = comps[g.comp];
+    SegHdr &h = P.segs[s];
+    h.comp = g.comp;
+    h.vbase = (GLOBAL || C.contiguous) ? (GLOBAL ? 0 : C.verts[0]) : -1;
+    h.nv = int32_t(C.verts.size());
+    h.x4off = GLOBAL ? C.verts[0] : x4off[g.comp];   // GLOBAL: the component's reference vertex (energy centring)
+    h.expected = nseg_of[g.comp];    // one "rows stored" signal per segment (sent by the CTA's last warp)
+    h.whole = (!GLOBAL && C.npos > P.vh) ? 1 : 0;
+    h.npos = C.npos;
+    h.p4off = GLOBAL ? 0 : p4off[g.comp];
+  }
+
+  // ---- per-warp streams ----------------------------------------------------------------------------------
+  P.wseg.assign(size_t(NS) * NW * 2, 0);
+  P.wdesc.assign(size_t(G) * NW * 2, 0);
+  std::vector<std::vector<uint8_t>> wstream(size_t(G) * NW);
+  std::vector<RowRef> rows;
+  std::vector<int> rb_of_warp[kMaxWarps];
+  LaneSlots lane_slots;
+  const int TPC = GLOBAL ? 32 : 64;                        // tets per tet cell
+  const double CTC = double(cfg.tetcell_cost) * (GLOBAL ? 0.6 : 1.0);
+  for (int b = 0; b < G; ++b) {
+    for (int s = P.cta_seg[2 * size_t(b)]; s < P.cta_seg[2 * size_t(b) + 1]; ++s) {
+      const Seg &g = segs[s];
+      const Comp &C = comps[g.comp];
+      const int32_t *gid = GLOBAL ? C.verts.data() : nullptr;
+      // where this segment's component will sit in the CTA's staging area (must match the kernel:
+      // "whole" components start at 0, others alternate between the two halves by position in the CTA)
+      const int li = s - P.cta_seg[2 * size_t(b)];
+      const bool whole = P.segs[s].whole != 0;
+      const int ubase_bytes = GLOBAL ? 0 : (whole ? 0 : (li & 1) * 2 * P.vh * 16);
+      const int xbase_bytes = GLOBAL ? 0 : ubase_bytes + (whole ? C.npos : P.vh) * 16;
+      if (!GLOBAL && xbase_bytes + C.npos * 16 > 65536) { err = "internal: staging offsets exceed 16 bits"; return TSB_E_INVALID; }
+      rows.clear();
+      for (int r = g.r0; r < g.r1; ++r) rows.push_back(RowRef{r, C.rptr[r + 1] - C.rptr[r]});
+      std::stable_sort(rows.begin(), rows.end(), [](const RowRef &a, const RowRef &c) { return a.len > c.len; });
+      // lanes per row: split rows until the segment has about one row block per warp
+      int L = 1;
+      while (L < cfg.max_lanes_per_row && (int(rows.size()) * L + 31) / 32 < NW) L *= 2;
+      while (L < 4 && !rows.empty() && rb_len4(rows.data(), 1, L) > 62) L *= 2;    // header field: len4 <= 62
+      if (!rows.empty() && rb_len4(rows.data(), 1, L) > 62) { err = "a vertex has more than 980 operator neighbours"; return TSB_E_MESH; }
+      const int RPB = 32 / L;                              // rows per block
+      const int nrb = (int(rows.size()) + RPB - 1) / RPB;
+      const int ntc = (g.t1 - g.t0 + TPC - 1) / TPC;
+      double load[kMaxWarps] = {0};
+      for (int w = 0; w < NW; ++w) rb_of_warp[w].clear();
+      for (int k = 0; k < nrb; ++k) {          // LPT: blocks arrive longest first
+        int w = int(std::min_element(load, load + NW) - load);
+        const int nr = std::min<int>(RPB, int(rows.size()) - k * RPB);
+        load[w] += double(rb_len4(rows.data() + size_t(k) * RPB, nr, L)) + 0.5;
+        rb_of_warp[w].push_back(k);
       }
+      int tc_cnt[kMaxWarps] = {0};
+      const int NWT = NW > 1 ? NW - 1 : 1;     // the last warp signals "rows stored" and takes no tets (it must never wait on itself)
+      for (int k = 0; k < ntc; ++k) {
+        int w = int(std::min_element(load, load + NWT) - load);
+        load[w] += CTC;
+        ++tc_cnt[w];
+      }
+      int tnext = g.t0;
+      for (int w = 0; w < NW; ++w) {
+        std::vector<uint8_t> &st = wstream[size_t(b) * NW + w];
+        for (int k : rb_of_warp[w]) {
+          const int nr = std::min<int>(RPB, int(rows.size()) - k * RPB);
+          const int len4 = GLOBAL ? emit_rb<uint32_t>(st, C, rows.data() + size_t(k) * RPB, nr, L, gid, 0, lane_slots, nullptr)
+                                  : emit_rb<uint16_t>(st, C, rows.data() + size_t(k) * RPB, nr, L, nullptr, ubase_bytes, lane_slots, P.gather_wavefronts);
+          P.nnz_padded += int64_t(len4) * 4 * 32;
+          P.n_cells += len4;
+        }
+        for (int k = 0; k < tc_cnt[w]; ++k) {
+          const int nt = std::min(TPC, g.t1 - tnext);
+          if (GLOBAL) emit_tc<uint32_t>(st, M, C, tnext, nt, 0, nullptr);
+          else emit_tc<uint16_t>(st, M, C, tnext, nt, xbase_bytes, P.tet_wavefronts);
+          tnext += nt;
+        }
+        if (rb_of_warp[w].size() > 0xFFFF || tc_cnt[w] > 0xFFFF) { err = "segment too large for the stream descriptors"; return TSB_E_INVALID; }
+        P.wseg[(size_t(s) * NW + w) * 2] = uint16_t(rb_of_warp[w].size());
+        P.wseg[(size_t(s) * NW + w) * 2 + 1] = uint16_t(tc_cnt[w]);
+      }
+      P.n_rb += nrb;
+      P.n_tetcells += ntc;
+      P.n_cells += ntc;
     }
-    // scratch slot of each row: vertex's slots are ordered by (tile, chunk)
-    for (int i = 0; i < nv; ++i) {
-      const int nr = int(row_of[i].size());
-      for (int c = 0; c < nr; ++c) slot[row_of[i][c]] = next_slot[vs[i]] + c;
-      next_slot[vs[i]] += nr;
-    }
+  }
+  size_t total = 0;
+  for (const auto &st : wstream) total += st.size();
+  if (total / 16 > 0xFFFFFFFFull) { err = "plan stream exceeds 64 GiB"; return TSB_E_NOMEM; }
+  P.stream.resize(std::max<size_t>(total, 16));
+  size_t off = 0;
+  for (size_t i = 0; i < wstream.size(); ++i) {
+    const auto &st = wstream[i];
+    if (!st.empty()) std::memcpy(P.stream.data() + off, st.data(), st.size());
+    P.wdesc[2 * i] = uint32_t(off / 16);
+    P.wdesc[2 * i + 1] = uint32_t(st.size());
+    if (st.size() > 0xFFFFFFFFull) { err = "warp stream exceeds 4 GiB"; return TSB_E_NOMEM; }
+    off += st.size();
   }
   return TSB_OK;
 }

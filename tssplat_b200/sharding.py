@@ -68,14 +68,14 @@ class ShardedEnergy:
     """
 
     def __init__(self, pack: TetPack, rank: Optional[int] = None, world_size: Optional[int] = None,
-                 device=None, group=None, tile_tets: int = 0):
+                 device=None, group=None, warps_per_cta: int = 0):
         from . import tet_spheres_ext as ext   # needs the CUDA library + a GPU
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.local, self.sphere_range = shard_pack(pack, self.rank, self.world_size)
         self.tet_sp = ext.TetSpheres(self.local.verts.reshape(-1), self.local.tets.reshape(-1),
-                                     device=device, tile_tets=tile_tets) if self.local.nele else None
+                                     device=device, warps_per_cta=warps_per_cta) if self.local.nele else None
         self._work = None
         self._comm_stream = torch.cuda.Stream(device=self.tet_sp.device) if self.tet_sp is not None else None
 

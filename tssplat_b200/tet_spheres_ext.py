@@ -35,6 +35,7 @@ from .mesh import load_veg
 __all__ = ["TetSpheres", "forward", "backward", "random_x", "grad_limit", "energy_grad_host"]
 
 return_cpu_scalar = False
+_limit_work = {}       # (device, stream) -> float32[4] scratch of grad_limit (caller-owned in the C ABI)
 #: compute the gradient inside ``forward`` (one launch per iteration) when ``x.requires_grad``
 fuse_backward_into_forward = True
 
@@ -52,8 +53,8 @@ class TetSpheres:
     (``tet_spheres.cpp:108-117``).
     """
 
-    def __init__(self, vertices, elements=None, *, device=None, tile_tets: int = 0,
-                 laplacian_scale: int = 0):
+    def __init__(self, vertices, elements=None, *, device=None, warps_per_cta: int = 0,
+                 laplacian_scale: int = 0, force_global: bool = False, ring_slots: int = 0):
         self._h = None
         if isinstance(vertices, (str, bytes)) and elements is None:
             v, t = load_veg(vertices if isinstance(vertices, str) else vertices.decode())
@@ -78,7 +79,8 @@ class TetSpheres:
             raise RuntimeError("tet_spheres_ext needs a CUDA device")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         torch.cuda.init()
-        opt = _capi.tsb_options_t(tile_tets=int(tile_tets), laplacian_scale=int(laplacian_scale))
+        opt = _capi.tsb_options_t(warps_per_cta=int(warps_per_cta), laplacian_scale=int(laplacian_scale),
+                                  ring_slots=int(ring_slots), force_global=int(bool(force_global)))
         h = C.c_void_p()
         rc = _capi.lib.tsb_create(vertices.ctypes.data, elements.ctypes.data, vertices.size // 3,
                                   elements.size // 4, C.byref(opt), self.device.index, C.byref(h))
@@ -198,7 +200,9 @@ def grad_limit(grad: torch.Tensor, s_threshold: float, s: float) -> None:
     (the intent of ``tet_spheres_cuda.cu:265-303``)."""
     if not grad.is_cuda or grad.dtype != torch.float32 or not grad.is_contiguous():
         raise RuntimeError("grad_limit needs a contiguous float32 CUDA tensor")
-    with torch.cuda.device(grad.device):
-        rc = _capi.lib.tsb_grad_limit(grad.data_ptr(), grad.numel(), float(s_threshold), float(s),
-                                      _stream_ptr(grad.device))
+    key = (grad.device.index, int(torch.cuda.current_stream(grad.device).cuda_stream))
+    work = _limit_work.get(key)
+    if work is None:
+        work = _limit_work[key] = torch.zeros(4, dtype=torch.float32, device=grad.device)
+    rc = _capi.lib.tsb_grad_limit(grad.data_ptr(), grad.numel(), float(s_threshold), float(s), work.data_ptr(), key[1])
     _capi.check(rc, None, "tet_spheres_ext.grad_limit")
