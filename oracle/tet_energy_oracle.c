@@ -19,7 +19,9 @@
  *                                               tet_spheres_cuda.cu:197-263, :68-102, :32-46
  *   order not in {2,4}: zero energy, zero gradient  (cu:57-63, 83-89)
  *
- * Build: see oracle/Makefile  (gcc -O2 -fopenmp -shared -fPIC).
+ * Build: see oracle/Makefile.  Three builds of this one file: the fp64 checker (portable -O2), and two
+ * TIMING builds for bench.py's CPU arms (-O3 -march=x86-64-v3, used only when the host has AVX2+FMA):
+ * fp64, and fp32 arithmetic (-DTSO_REAL=float: the reference's own precision, tet_spheres.cpp:43-45).
  */
 #include <math.h>
 #include <stdint.h>
@@ -29,17 +31,22 @@
 #include <omp.h>
 #endif
 
+#ifndef TSO_REAL
+#define TSO_REAL double
+#endif
+typedef TSO_REAL real;   /* arithmetic type of the per-tet passes (the checker build uses double) */
+
 typedef struct {
   int n, nele, scale;
   int *tets;      /* nele*4 */
   int *nbr;       /* nele*4, -1 = boundary; face k is opposite local vertex k */
-  double *B;      /* nele*9, row-major Dm^-1 */
-  double *w;      /* nele, Laplacian row scale (1 or 1/deg) */
+  real *B;        /* nele*9, row-major Dm^-1 */
+  real *w;        /* nele, Laplacian row scale (1 or 1/deg) */
   int *deg;       /* nele */
   int *inc_ptr;   /* n+1  : vertex -> incident (tet*4+slot) */
   int *inc;       /* nele*4 */
-  double *F, *H, *P;  /* nele*9 scratch */
-  double *contrib;    /* nele*12 */
+  real *F, *H, *P;    /* nele*9 scratch */
+  real *contrib;      /* nele*12 */
 } TsoOracle;
 
 typedef struct { int64_t a, b, c; int owner; } FaceKey;
@@ -84,13 +91,13 @@ TsoOracle *tso_create(const float *rest, const int *tets, int n, int nele, int l
   o->tets = (int *)malloc(sizeof(int) * 4 * (size_t)nele);
   memcpy(o->tets, tets, sizeof(int) * 4 * (size_t)nele);
   o->nbr = (int *)malloc(sizeof(int) * 4 * (size_t)nele);
-  o->B = (double *)malloc(sizeof(double) * 9 * (size_t)nele);
-  o->w = (double *)malloc(sizeof(double) * (size_t)nele);
+  o->B = (real *)malloc(sizeof(real) * 9 * (size_t)nele);
+  o->w = (real *)malloc(sizeof(real) * (size_t)nele);
   o->deg = (int *)malloc(sizeof(int) * (size_t)nele);
-  o->F = (double *)malloc(sizeof(double) * 9 * (size_t)nele);
-  o->H = (double *)malloc(sizeof(double) * 9 * (size_t)nele);
-  o->P = (double *)malloc(sizeof(double) * 9 * (size_t)nele);
-  o->contrib = (double *)malloc(sizeof(double) * 12 * (size_t)nele);
+  o->F = (real *)malloc(sizeof(real) * 9 * (size_t)nele);
+  o->H = (real *)malloc(sizeof(real) * 9 * (size_t)nele);
+  o->P = (real *)malloc(sizeof(real) * 9 * (size_t)nele);
+  o->contrib = (real *)malloc(sizeof(real) * 12 * (size_t)nele);
   for (int t = 0; t < nele; t++) {
     const int *v = tets + 4 * t;
     for (int k = 0; k < 4; k++) if (v[k] < 0 || v[k] >= n) { tso_destroy(o); return NULL; }
@@ -98,7 +105,9 @@ TsoOracle *tso_create(const float *rest, const int *tets, int n, int nele, int l
     for (int r = 0; r < 3; r++)
       for (int k = 0; k < 3; k++)
         Dm[3 * r + k] = (double)rest[3 * v[k + 1] + r] - (double)rest[3 * v[0] + r];
-    if (inv3(Dm, o->B + 9 * t)) { tso_destroy(o); return NULL; }
+    double Bd[9];
+    if (inv3(Dm, Bd)) { tso_destroy(o); return NULL; }
+    for (int i = 0; i < 9; i++) o->B[9 * t + i] = (real)Bd[i];     /* fp64 -> working precision (tet_spheres.cpp:43-45) */
   }
   /* face adjacency by sorting face keys */
   FaceKey *fk = (FaceKey *)malloc(sizeof(FaceKey) * 4 * (size_t)nele);
@@ -124,7 +133,7 @@ TsoOracle *tso_create(const float *rest, const int *tets, int n, int nele, int l
     int d = 0;
     for (int k = 0; k < 4; k++) d += o->nbr[4 * t + k] >= 0;
     o->deg[t] = d;
-    o->w[t] = laplacian_scale ? (d > 0 ? 1.0 / d : 0.0) : 1.0;
+    o->w[t] = (real)(laplacian_scale ? (d > 0 ? 1.0 / d : 0.0) : 1.0);
   }
   /* vertex incidence CSR */
   o->inc_ptr = (int *)calloc((size_t)n + 1, sizeof(int));
@@ -138,6 +147,8 @@ TsoOracle *tso_create(const float *rest, const int *tets, int n, int nele, int l
   return o;
 }
 
+int tso_real_bytes(void) { return (int)sizeof(real); }
+
 int tso_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -146,12 +157,12 @@ int tso_num_threads(void) {
 #endif
 }
 
-static inline double det3(const double *F) {
+static inline real det3(const real *F) {
   return F[0] * (F[4] * F[8] - F[5] * F[7]) - F[1] * (F[3] * F[8] - F[5] * F[6]) + F[2] * (F[3] * F[7] - F[4] * F[6]);
 }
 
 /* d det / dF, row-major (tet_spheres_cuda.cu:32-46) */
-static inline void cof3(const double *F, double *C) {
+static inline void cof3(const real *F, real *C) {
   C[0] = F[4] * F[8] - F[5] * F[7]; C[1] = F[5] * F[6] - F[3] * F[8]; C[2] = F[3] * F[7] - F[4] * F[6];
   C[3] = F[2] * F[7] - F[1] * F[8]; C[4] = F[0] * F[8] - F[2] * F[6]; C[5] = F[1] * F[6] - F[0] * F[7];
   C[6] = F[1] * F[5] - F[2] * F[4]; C[7] = F[2] * F[3] - F[0] * F[5]; C[8] = F[0] * F[4] - F[1] * F[3];
@@ -171,55 +182,55 @@ int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int orde
 #pragma omp for schedule(static)
     for (int t = 0; t < nele; t++) {
       const int *v = o->tets + 4 * t;
-      const double *B = o->B + 9 * t;
-      double Ds[9];
+      const real *B = o->B + 9 * t;
+      real Ds[9];
       for (int r = 0; r < 3; r++)
-        for (int k = 0; k < 3; k++) Ds[3 * r + k] = (double)x[3 * v[k + 1] + r] - (double)x[3 * v[0] + r];
-      double *F = o->F + 9 * t;
+        for (int k = 0; k < 3; k++) Ds[3 * r + k] = (real)x[3 * v[k + 1] + r] - (real)x[3 * v[0] + r];
+      real *F = o->F + 9 * t;
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) F[3 * r + c] = Ds[3 * r] * B[c] + Ds[3 * r + 1] * B[3 + c] + Ds[3 * r + 2] * B[6 + c];
     }
 #pragma omp for schedule(static) reduction(+ : sm)
     for (int t = 0; t < nele; t++) {
-      double *H = o->H + 9 * t;
-      const double *F = o->F + 9 * t;
+      real *H = o->H + 9 * t;
+      const real *F = o->F + 9 * t;
       for (int i = 0; i < 9; i++) H[i] = o->deg[t] * F[i];
       for (int k = 0; k < 4; k++) {
         int s = o->nbr[4 * t + k];
         if (s >= 0) for (int i = 0; i < 9; i++) H[i] -= o->F[9 * s + i];
       }
-      double e = 0.0;
+      real e = 0;
       for (int i = 0; i < 9; i++) { H[i] *= o->w[t]; e += H[i] * H[i]; }
-      sm += 0.5 * e;
+      sm += 0.5 * (double)e;
     }
 #pragma omp for schedule(static) reduction(+ : bar)
     for (int t = 0; t < nele; t++) {
       /* P = c1 * (L^T H)_t + c2 * D_t ;  (L^T H)_t = deg_t w_t H_t - sum_s w_s H_s */
-      double P[9];
-      const double *H = o->H + 9 * t;       /* H_t = w_t (deg_t F_t - sum F_s), stored scaled */
+      real P[9];
+      const real *H = o->H + 9 * t;         /* H_t = w_t (deg_t F_t - sum F_s), stored scaled */
       for (int i = 0; i < 9; i++) P[i] = o->deg[t] * o->w[t] * H[i];
       for (int k = 0; k < 4; k++) {
         int s = o->nbr[4 * t + k];
         if (s >= 0) for (int i = 0; i < 9; i++) P[i] -= o->w[s] * o->H[9 * s + i];
       }
-      for (int i = 0; i < 9; i++) P[i] *= c1;
-      const double *F = o->F + 9 * t;
-      double J = det3(F);
-      if (J < 0.0) {
-        double m = -J, e = 0.0, coef = 0.0, C[9];
-        if (order == 2) { e = m * m; coef = 2.0 * m; }
-        else if (order == 4) { e = m * m * m * m; coef = 4.0 * m * m * m; }
-        bar += e;
+      for (int i = 0; i < 9; i++) P[i] *= (real)c1;
+      const real *F = o->F + 9 * t;
+      real J = det3(F);
+      if (J < 0) {
+        real m = -J, e = 0, coef = 0, C[9];
+        if (order == 2) { e = m * m; coef = 2 * m; }
+        else if (order == 4) { e = m * m * m * m; coef = 4 * m * m * m; }
+        bar += (double)e;
         cof3(F, C);
-        for (int i = 0; i < 9; i++) P[i] += c2 * (-coef) * C[i];
+        for (int i = 0; i < 9; i++) P[i] += (real)c2 * (-coef) * C[i];
       }
       /* dE/dx_k = P a_k,  a_k = row k-1 of B (k=1..3), a_0 = -(a_1+a_2+a_3) */
-      const double *B = o->B + 9 * t;
-      double *cb = o->contrib + 12 * t;
+      const real *B = o->B + 9 * t;
+      real *cb = o->contrib + 12 * t;
       for (int r = 0; r < 3; r++) {
-        double s0 = 0.0;
+        real s0 = 0;
         for (int k = 0; k < 3; k++) {
-          double g = P[3 * r] * B[3 * k] + P[3 * r + 1] * B[3 * k + 1] + P[3 * r + 2] * B[3 * k + 2];
+          real g = P[3 * r] * B[3 * k] + P[3 * r + 1] * B[3 * k + 1] + P[3 * r + 2] * B[3 * k + 2];
           cb[3 * (k + 1) + r] = g;
           s0 -= g;
         }
@@ -229,12 +240,12 @@ int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int orde
     if (grad) {
 #pragma omp for schedule(static)
       for (int v = 0; v < n; v++) {
-        double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+        real g0 = 0, g1 = 0, g2 = 0;
         for (int e = o->inc_ptr[v]; e < o->inc_ptr[v + 1]; e++) {
-          const double *cb = o->contrib + 3 * (size_t)o->inc[e];
+          const real *cb = o->contrib + 3 * (size_t)o->inc[e];
           g0 += cb[0]; g1 += cb[1]; g2 += cb[2];
         }
-        grad[3 * v] = gradH * g0; grad[3 * v + 1] = gradH * g1; grad[3 * v + 2] = gradH * g2;
+        grad[3 * v] = gradH * (double)g0; grad[3 * v + 1] = gradH * (double)g1; grad[3 * v + 2] = gradH * (double)g2;
       }
     }
   }

@@ -12,11 +12,21 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 ORACLE_SO = os.path.join(ROOT, "oracle", "libtet_energy_oracle.so")
 
 
-class COracle:
-    """oracle/tet_energy_oracle.c through ctypes."""
+def host_has_avx2_fma() -> bool:
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return " avx2" in flags and " fma" in flags
+    except OSError:
+        return False
 
-    def __init__(self, rest, tets, laplacian_scale=0):
-        self.lib = C.CDLL(ORACLE_SO)
+
+class COracle:
+    """oracle/tet_energy_oracle.c through ctypes.  variant: "" = the fp64 checker; "fast" / "fast32" = the
+    AVX2 timing builds (fp64 / fp32 arithmetic) used by bench.py's CPU arms only."""
+
+    def __init__(self, rest, tets, laplacian_scale=0, variant=""):
+        so = ORACLE_SO if not variant else ORACLE_SO.replace(".so", f"_{variant}.so")
+        self.lib = C.CDLL(so)
         self.lib.tso_create.restype = C.c_void_p
         self.lib.tso_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         self.lib.tso_destroy.argtypes = [C.c_void_p]

@@ -2,6 +2,7 @@
 // so the CPU test-suite can re-enact the kernel's stream walk in numpy and compare it with the oracle
 // without a GPU.  Built into tests/native/libtsb_plan_debug.so by __graft_entry__.build(); never part
 // of libtssplat_b200.so.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -25,6 +26,7 @@ int tsbdbg_build(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t 
   if (vh_cap > 0) pc.vh_cap = vh_cap;
   if (area_cap > 0) pc.area_cap = area_cap;
   if (tet_cost > 0) pc.tet_cost = tet_cost;
+  if (const char *e = std::getenv("TSB_RB_CAP_DIV")) pc.rb_cap_div = std::atoi(e);
   tsbdbg_plan *d = new tsbdbg_plan();
   const int rc = tsb::build_plan(rest_xyz, tets, n, nele, pc, d->plan, g_err);
   if (rc != TSB_OK) { delete d; return rc; }

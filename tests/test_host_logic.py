@@ -29,26 +29,65 @@ def test_info_struct_matches_header():
     assert fields == [f for f, _ in _capi.tsb_info_t._fields_]
 
 
-@pytest.mark.parametrize("tile_tets,balance", [(256, 0), (512, 0), (512, 5), (1024, 0)])
-def test_plan_reenactment_matches_oracle(tile_tets, balance):
+PLAN_VARIANTS = [dict(nw=16, grid=148), dict(nw=8, grid=5), dict(nw=16, grid=7, force_global=1),
+                 dict(nw=8, grid=3, vh_cap=100, area_cap=300),        # components staged in the "whole area" mode
+                 dict(nw=16, grid=1), dict(nw=8, grid=296)]
+
+
+@pytest.mark.parametrize("kw", PLAN_VARIANTS, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_plan_reenactment_matches_oracle(kw):
+    """The product's plan builder (operator rows, bank-aware placement, segments, warp streams) walked in
+    numpy exactly as the kernel walks it, against the fp64 C oracle."""
     pack = make_pack(3, 768, seed=2)
-    plan = build_host_plan(pack.verts, pack.tets, tile_tets, balance_sms=balance)
-    assert sorted(plan["tet_order"].tolist()) == list(range(pack.nele))      # every tet exactly once
-    assert sum(int(t["ntet"]) for t in plan["tiles"]) == pack.nele
-    assert plan["n_components"] == 3
+    plan = build_host_plan(pack.verts, pack.tets, **kw)
+    assert plan["n_components"] == 3 and plan["mode_global"] == kw.get("force_global", 0)
     orc = COracle(pack.verts, pack.tets)
     for sig, order in ((0.02, 2), (0.35, 4)):
         x = perturb(pack, sigma_rel=sig, seed=1)
         E, es, eb, g = emulate_kernel(plan, x, 2e-4, 3e-4, order, gradH=0.7)
         Eo, terms, go = orc.energy_grad(x, 2e-4, 3e-4, order, gradH=0.7)
-        assert E == pytest.approx(Eo, rel=2e-6)          # fp32 rest inverses, fp64 arithmetic
+        assert E == pytest.approx(Eo, rel=2e-6)          # fp32 operator entries, fp64 arithmetic
+        assert es == pytest.approx(terms[0], rel=2e-6) and eb == pytest.approx(terms[1], rel=2e-6, abs=1e-300)
         assert np.linalg.norm(g - go) <= 2e-6 * np.linalg.norm(go)
+
+
+def test_plan_operator_is_the_reference_matrix():
+    """The streamed rows are M = G^T L^T L G (tet_spheres.cpp:148) minus its diagonal: rebuild M from the
+    stream and compare with the scipy operator of the oracle, entry by entry."""
+    from oracle.tet_energy_oracle import ReferenceEnergyOracle
+    v, t = make_tet_sphere(1201, 300)
+    plan = build_host_plan(v, t, nw=8, grid=3)
+    M = ReferenceEnergyOracle(v.astype(np.float32), t).M.tocsr()[0::3, :][:, 0::3].toarray()
+    n = len(v)
+    R = np.zeros((n, n))
+    x = np.zeros((n, 3), dtype=np.float32)
+    X = v.astype(np.float32)
+    for j in range(n):                                  # column j of the operator = gradient for u = e_j (x-coordinate)
+        x[:] = X
+        x[j, 0] += 1.0
+        _, _, _, g = emulate_kernel(plan, x, 1.0, 0.0, 2)
+        R[:, j] = g[:, 0]
+    assert np.abs(R - M).max() <= 2e-6 * np.abs(M).max()
+    assert np.abs(R.sum(axis=1)).max() <= 1e-4 * np.abs(M).max()        # zero row sums (difference form)
+
+
+def test_plan_bank_placement_and_slot_colouring():
+    """Bank-aware staging: positions are a permutation, every row's columns are spread over the 8 bank
+    groups, and the slot assignment keeps the quarter-warp gathers (nearly) conflict free."""
+    pack = make_pack(4, 2048, seed=5)
+    plan = build_host_plan(pack.verts, pack.tets, nw=16, grid=37)
+    assert plan["gather_wf"] <= 1.15 * plan["gather_wf_ideal"]
+    for sg in plan["segs"]:
+        pos = plan["pos16"][sg["x4off"]:sg["x4off"] + sg["nv"]]
+        assert len(set(pos.tolist())) == sg["nv"] and pos.max() < sg["npos"] <= sg["nv"] + 64
+        assert np.bincount(pos % 8, minlength=8).min() >= sg["nv"] // 8 - 8
 
 
 def test_plan_laplacian_scale_and_unreferenced_vertices():
     v, t = make_tet_sphere(1201, 300)
     v = np.concatenate([v, [[5.0, 5.0, 5.0], [6.0, 6.0, 6.0]]])          # two vertices no tet uses
-    plan = build_host_plan(v, t, 256, laplacian_scale=1)
+    plan = build_host_plan(v, t, nw=8, grid=4, laplacian_scale=1)
+    assert sorted(plan["orphans"].tolist()) == [len(v) - 2, len(v) - 1]
     x = perturb(v, t, 0.3, 7)
     E, _, _, g = emulate_kernel(plan, x, 1e-3, 1e-3, 2)
     Eo, _, go = COracle(v, t, 1).energy_grad(x, 1e-3, 1e-3, 2)
@@ -57,9 +96,28 @@ def test_plan_laplacian_scale_and_unreferenced_vertices():
     assert np.linalg.norm(g - go) <= 2e-6 * np.linalg.norm(go)
 
 
+def test_plan_noncontiguous_components():
+    """Two spheres whose vertices are interleaved in the caller's numbering (vlist path)."""
+    pk = make_pack(2, 400, seed=11)
+    n = pk.n
+    perm = np.random.default_rng(0).permutation(n)                        # new id of old vertex
+    verts = np.empty_like(pk.verts)
+    verts[perm] = pk.verts
+    tets = perm[pk.tets].astype(np.int32)
+    plan = build_host_plan(verts, tets, nw=8, grid=6)
+    assert plan["contiguous"] == 0 and plan["n_components"] == 2
+    x = perturb(verts, tets, 0.3, 3)
+    E, _, _, g = emulate_kernel(plan, x, 1e-3, 2e-3, 4)
+    Eo, _, go = COracle(verts, tets).energy_grad(x, 1e-3, 2e-3, 4)
+    assert E == pytest.approx(Eo, rel=2e-6) and np.linalg.norm(g - go) <= 2e-6 * np.linalg.norm(go)
+
+
 def test_plan_real_mesh_a_veg():
+    """The reference's only in-tree mesh (tssplat_ext/a.veg, 4500 vertices in one component): too large to
+    stage in shared memory, so it runs in the global-gather mode."""
     d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
-    plan = build_host_plan(d["verts"], d["tets"], 512, balance_sms=0)
+    plan = build_host_plan(d["verts"], d["tets"], nw=16, grid=148)
+    assert plan["mode_global"] == 1
     x = perturb(d["verts"], d["tets"], 0.35, 1)
     E, es, eb, g = emulate_kernel(plan, x, 3.2e-3, 3.2e-3, 2, gradH=0.5)
     gold = np.load(os.path.join(GOLDEN, "golden_energy.npz"))
@@ -72,20 +130,19 @@ def test_tiny_meshes():
     v1 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)
     t1 = np.array([[0, 1, 2, 3]], dtype=np.int32)
     x = (v1 * np.array([1, 1, -1.5])).astype(np.float32)
-    E, es, eb, g = emulate_kernel(build_host_plan(v1, t1, 256), x, 1.0, 1.0, 2)
+    E, es, eb, g = emulate_kernel(build_host_plan(v1, t1, nw=8, grid=2), x, 1.0, 1.0, 2)
     assert es == 0.0 and eb == pytest.approx(1.5 ** 2)
     v2 = np.concatenate([v1, [[1.0, 1.0, 1.0]]])
-    t2 = np.array([[0, 1, 2, 3], [1, 2, 3, 4]], dtype=np.int32)
-    t2[1] = [1, 3, 2, 4]                                                   # positive orientation
+    t2 = np.array([[0, 1, 2, 3], [1, 3, 2, 4]], dtype=np.int32)             # positive orientation
     x2 = perturb(v2, t2, 0.3, 1)
-    E2, _, _, g2 = emulate_kernel(build_host_plan(v2, t2, 256), x2, 0.7, 0.3, 2)
+    E2, _, _, g2 = emulate_kernel(build_host_plan(v2, t2, nw=8, grid=2), x2, 0.7, 0.3, 2)
     Eo, _, go = COracle(v2, t2).energy_grad(x2, 0.7, 0.3, 2)
     assert E2 == pytest.approx(Eo, rel=1e-5) and np.abs(g2 - go).max() < 1e-5 * np.abs(go).max()
 
 
 def _plan_error(v, t):
     with pytest.raises(RuntimeError) as ei:
-        build_host_plan(np.asarray(v, dtype=np.float64), np.asarray(t, dtype=np.int32), 256)
+        build_host_plan(np.asarray(v, dtype=np.float64), np.asarray(t, dtype=np.int32), nw=8, grid=4)
     return str(ei.value)
 
 
@@ -99,10 +156,12 @@ def test_plan_rejects_bad_meshes():
     assert "non-manifold" in _plan_error(vv, three)
 
 
-def test_unsupported_tile_size():
+def test_bad_plan_configuration():
     v, t = make_tet_sphere(1202, 64)
     with pytest.raises(RuntimeError):
-        build_host_plan(v, t, 300)
+        build_host_plan(v, t, nw=64, grid=4)            # more warps than the kernel variants have
+    with pytest.raises(RuntimeError):
+        build_host_plan(v, t, nw=8, grid=0)
 
 
 def test_veg_round_trip(tmp_path):

@@ -168,3 +168,49 @@ def test_vanilla_pytorch_restatement_single_sphere():
         eo, _, go = COracle(v, t).energy_grad(x_np, 2e-4, 2e-4, order)
         assert float(e) == pytest.approx(eo, rel=2e-4)
         assert np.linalg.norm(x.grad.numpy() - go) <= 2e-3 * np.linalg.norm(go)
+
+
+# ---- pinned to reference-held code: fixtures generated by tests/golden/make_ref_fixtures.py from the
+# reference's own geometry/mesh_utils.py (compute_G_matrix) imported in the build container ---------------
+@pytest.fixture(scope="module")
+def ref_fix():
+    return np.load(os.path.join(GOLDEN, "ref_fixtures.npz"))
+
+
+def _ref_meshes(aveg):
+    from tssplat_b200.mesh import make_pack
+    pk = make_pack(3, 1024, seed=1)
+    return {"a_veg": (aveg[0].astype(np.float32), aveg[1]), "pack3x1024": (pk.verts, pk.tets)}
+
+
+def test_oracle_F_matches_reference_compute_G_matrix(aveg, ref_fix):
+    """SURVEY section 4 test 7: the restated F = Ds Dm^-1 equals compute_G_matrix(...) @ x_local
+    (geometry/mesh_utils.py:38-69) to fp64 round-off, on a.veg and on a synthetic pack."""
+    for name, (v32, t) in _ref_meshes(aveg).items():
+        V = v32.astype(np.float64)
+        B = rest_inverse(V, t)
+        G = build_G(V, t)
+        for case in ("benign", "inverted"):
+            x = ref_fix[f"{name}/{case}/x"].astype(np.float64)
+            F = deformation_gradients(x, t, B).reshape(-1, 9)
+            step = max(1, len(t) // 512)
+            assert np.abs(F[::step][:512] - ref_fix[f"{name}/{case}/F_sample"]).max() < 1e-10
+            det = np.linalg.det(F.reshape(-1, 3, 3))
+            assert np.abs(det - ref_fix[f"{name}/{case}/detF"]).max() < 1e-10
+            Fg = (G @ x.reshape(-1)).reshape(-1, 9)
+            assert np.abs(Fg[::step][:512] - ref_fix[f"{name}/{case}/F_sample"]).max() < 1e-10
+
+
+def test_oracle_barrier_matches_reference_F(aveg, ref_fix):
+    """Barrier sum of both oracles == sum max(-det F, 0)^p evaluated on the REFERENCE's F
+    (tet_spheres_cuda.cu:48-66 applied to compute_G_matrix's output)."""
+    for name, (v32, t) in _ref_meshes(aveg).items():
+        o1, o2 = ReferenceEnergyOracle(v32, t), COracle(v32, t)
+        for case in ("benign", "inverted"):
+            x = ref_fix[f"{name}/{case}/x"]
+            for order in (2, 4):
+                want = float(ref_fix[f"{name}/{case}/barrier_o{order}"])
+                _, bar = o1.energy_terms(x, order)
+                _, terms, _ = o2.energy_grad(x, 1.0, 1.0, order, want_grad=False)
+                assert float(bar) == pytest.approx(want, rel=1e-9, abs=1e-300)
+                assert terms[1] == pytest.approx(want, rel=1e-9, abs=1e-300)

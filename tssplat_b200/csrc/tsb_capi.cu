@@ -156,6 +156,8 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     return ch.ctas * sms;
   };
 
+  pc.ring_cells = env_int("TSSPLAT_B200_NO_SPLIT", 0) ? 0 : ring * cpc;
+  pc.rb_cap_div = std::max(1, env_int("TSSPLAT_B200_RB_CAP_DIV", pc.rb_cap_div));
   tsb::HostPlan plan;
   std::string err;
   int rc = tsb::build_plan(rest_xyz, tets, n, nele, pc, plan, err);

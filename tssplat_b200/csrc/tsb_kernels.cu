@@ -28,6 +28,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 #include "tsb_kernels.cuh"
 
@@ -596,7 +597,8 @@ cudaError_t launch_variant(const KParams &p, const LaunchConfig &lc, cudaStream_
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int no_pdl = std::getenv("TSSPLAT_B200_NO_PDL") != nullptr;     // developer A/B switch
+  attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, energy_grad_kernel<NW, MINB, GLOBAL>, p);

@@ -728,6 +728,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   LaneSlots lane_slots;
   const int TPC = GLOBAL ? 32 : 64;                        // tets per tet cell
   const double CTC = double(cfg.tetcell_cost) * (GLOBAL ? 0.6 : 1.0);
+  double load[kMaxWarps] = {0};
   for (int b = 0; b < G; ++b) {
     for (int s = P.cta_seg[2 * size_t(b)]; s < P.cta_seg[2 * size_t(b) + 1]; ++s) {
       const Seg &g = segs[s];
@@ -743,36 +744,58 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       rows.clear();
       for (int r = g.r0; r < g.r1; ++r) rows.push_back(RowRef{r, C.rptr[r + 1] - C.rptr[r]});
       std::stable_sort(rows.begin(), rows.end(), [](const RowRef &a, const RowRef &c) { return a.len > c.len; });
-      // lanes per row: split rows until the segment has about one row block per warp
-      int L = 1;
-      while (L < cfg.max_lanes_per_row && (int(rows.size()) * L + 31) / 32 < NW) L *= 2;
-      while (L < 4 && !rows.empty() && rb_len4(rows.data(), 1, L) > 62) L *= 2;    // header field: len4 <= 62
-      if (!rows.empty() && rb_len4(rows.data(), 1, L) > 62) { err = "a vertex has more than 980 operator neighbours"; return TSB_E_MESH; }
-      const int RPB = 32 / L;                              // rows per block
-      const int nrb = (int(rows.size()) + RPB - 1) / RPB;
+      // Row blocks.  L lanes per row (1, 2 or 4) is chosen PER BLOCK: in the latency regime (the CTA's whole
+      // work fits the per-warp TMA rings, so nothing is ever refilled mid-kernel) long rows are split over
+      // adjacent lanes until a block is at most `rb_cap` quad cells, which bounds every warp's serial chain;
+      // in the streaming regime blocks are never split (fewest padded entries).
+      struct RB { int first, nrows, L, len4; };
+      std::vector<RB> rbs;
+      bool seg_latency = false;
+      {
+        const int ntc_total = (g.t1 - g.t0 + TPC - 1) / TPC;
+        int64_t cells1 = ntc_total;                        // cells of this segment with L = 1 everywhere
+        for (size_t i = 0; i < rows.size(); i += 32) cells1 += rb_len4(rows.data() + i, int(std::min<size_t>(32, rows.size() - i)), 1);
+        const bool latency_regime = cfg.ring_cells > 0 && cells1 * 10 <= int64_t(cfg.ring_cells) * NW * 9;
+        const int rb_cap = latency_regime ? std::max(3, cfg.ring_cells / cfg.rb_cap_div) : 62;
+        seg_latency = latency_regime;
+        size_t i = 0;
+        while (i < rows.size()) {
+          int L = 1;
+          while (L < 4 && rb_len4(rows.data() + i, 1, L) > (L < cfg.max_lanes_per_row ? rb_cap : 62)) L *= 2;
+          if (rb_len4(rows.data() + i, 1, L) > 62) { err = "a vertex has more than 980 operator neighbours"; return TSB_E_MESH; }
+          const int nr = int(std::min<size_t>(size_t(32 / L), rows.size() - i));
+          rbs.push_back(RB{int(i), nr, L, rb_len4(rows.data() + i, nr, L)});
+          i += nr;
+        }
+      }
+      const int nrb = int(rbs.size());
       const int ntc = (g.t1 - g.t0 + TPC - 1) / TPC;
-      double load[kMaxWarps] = {0};
-      for (int w = 0; w < NW; ++w) rb_of_warp[w].clear();
-      for (int k = 0; k < nrb; ++k) {          // LPT: blocks arrive longest first
-        int w = int(std::min_element(load, load + NW) - load);
-        const int nr = std::min<int>(RPB, int(rows.size()) - k * RPB);
-        load[w] += double(rb_len4(rows.data() + size_t(k) * RPB, nr, L)) + 0.5;
-        rb_of_warp[w].push_back(k);
+      if (s == P.cta_seg[2 * size_t(b)]) for (int w = 0; w < NW; ++w) load[w] = 0.0;   // loads carry over the CTA's segments:
+      for (int w = 0; w < NW; ++w) rb_of_warp[w].clear();                               // balances every warp's whole stream
+      {
+        std::vector<int> order(nrb);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rbs[a].len4 > rbs[b].len4; });
+        for (int k : order) {                  // LPT: longest block first
+          int w = int(std::min_element(load, load + NW) - load);
+          load[w] += double(rbs[k].len4) + (seg_latency ? 0.0 : 0.5);
+          rb_of_warp[w].push_back(k);
+        }
       }
       int tc_cnt[kMaxWarps] = {0};
       const int NWT = NW > 1 ? NW - 1 : 1;     // the last warp signals "rows stored" and takes no tets (it must never wait on itself)
       for (int k = 0; k < ntc; ++k) {
         int w = int(std::min_element(load, load + NWT) - load);
-        load[w] += CTC;
+        load[w] += seg_latency ? 1.0 : CTC;     // latency regime: balance the CELL count so that every stream fits its ring
         ++tc_cnt[w];
       }
       int tnext = g.t0;
       for (int w = 0; w < NW; ++w) {
         std::vector<uint8_t> &st = wstream[size_t(b) * NW + w];
         for (int k : rb_of_warp[w]) {
-          const int nr = std::min<int>(RPB, int(rows.size()) - k * RPB);
-          const int len4 = GLOBAL ? emit_rb<uint32_t>(st, C, rows.data() + size_t(k) * RPB, nr, L, gid, 0, lane_slots, nullptr)
-                                  : emit_rb<uint16_t>(st, C, rows.data() + size_t(k) * RPB, nr, L, nullptr, ubase_bytes, lane_slots, P.gather_wavefronts);
+          const RB &rb = rbs[k];
+          const int len4 = GLOBAL ? emit_rb<uint32_t>(st, C, rows.data() + rb.first, rb.nrows, rb.L, gid, 0, lane_slots, nullptr)
+                                  : emit_rb<uint16_t>(st, C, rows.data() + rb.first, rb.nrows, rb.L, nullptr, ubase_bytes, lane_slots, P.gather_wavefronts);
           P.nnz_padded += int64_t(len4) * 4 * 32;
           P.n_cells += len4;
         }

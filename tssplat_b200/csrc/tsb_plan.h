@@ -76,7 +76,9 @@ struct PlanConfig {
   int32_t force_global = 0;     // 1: skip staging, gather from global memory (testing / huge components)
   float tet_cost = 3.0f;        // cost of one tet relative to one operator entry (CTA-level cut)
   float tetcell_cost = 1.3f;    // cost of one tet cell relative to one quad cell (warp-level deal)
-  int32_t max_lanes_per_row = 1;   // > 1: split rows over adjacent lanes when a segment has few row blocks
+  int32_t max_lanes_per_row = 4;   // rows may be split over up to this many adjacent lanes (latency regime only)
+  int32_t ring_cells = 12;         // cells one warp's TMA ring holds (decides the latency / streaming regime)
+  int32_t rb_cap_div = 2;          // latency regime: a row block is at most ring_cells / rb_cap_div cells
   int32_t threads = 0;          // host threads for the build (0 = hardware concurrency, capped)
 };
 

@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _capi
+from . import tet_spheres_ext as _ext
 
 __all__ = ["AdamUniform"]
 
@@ -68,4 +69,5 @@ class AdamUniform(torch.optim.Optimizer):
                         float(lr), float(b1), float(b2), int(state["step"]), limit, state["_work"].data_ptr(),
                         int(torch.cuda.current_stream(p.device).cuda_stream))
                 _capi.check(rc, None, "AdamUniform.step")
+                _ext.note_parameters_changed()         # p.data changed without bumping p._version
                 self.cc += 1                                   # :89

@@ -94,6 +94,9 @@ class TetSpheres:
         self.n3 = 3 * self.n
         self._cache_key = None
         self._cache_grad: Optional[torch.Tensor] = None
+        # energies of the last 32 launches (a ring, so a loss tensor stays valid while it is being logged)
+        self._energy_ring = torch.zeros((32, 3), dtype=torch.float32, device=self.device)
+        self._ring_i = 0
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -111,13 +114,16 @@ class TetSpheres:
             raise RuntimeError(f"vertexPositions is on {x.device}, TetSpheres on {self.device}")
         if x.numel() != self.n3:
             raise RuntimeError(f"vertexPositions has {x.numel()} entries, expected {self.n3}")
-        return x.detach().contiguous()            # tet_spheres_cuda.cu:124
+        return x if x.is_contiguous() else x.contiguous()            # tet_spheres_cuda.cu:124
 
     def energy_grad(self, x: torch.Tensor, c1: float, c2: float, order: int, gradH=1.0,
                     want_grad: bool = True):
-        """The fused launch.  Returns (energy[3] = total/smooth/barrier on device, grad or None)."""
+        """The fused launch.  Returns (energy[3] = total/smooth/barrier on device, grad or None).
+        The energy tensor is a slot of a 32-deep ring owned by the handle (no allocation per call)."""
         xc = self._check_x(x)
-        energy = torch.empty(3, dtype=torch.float32, device=self.device)
+        i = self._ring_i
+        self._ring_i = (i + 1) & 31
+        energy = self._energy_ring[i]
         grad = torch.empty((self.n, 3), dtype=torch.float32, device=self.device) if want_grad else None
         gh_val, gh_ptr, keep = 1.0, None, None
         if isinstance(gradH, torch.Tensor):
@@ -131,7 +137,8 @@ class TetSpheres:
         rc = _capi.lib.tsb_energy_grad(self._h, xc.data_ptr(), float(c1), float(c2), int(order), gh_val,
                                        gh_ptr, energy.data_ptr(), grad.data_ptr() if want_grad else None,
                                        _stream_ptr(self.device))
-        _capi.check(rc, self._h, "tet_spheres_ext")
+        if rc:
+            _capi.check(rc, self._h, "tet_spheres_ext")
         del keep
         return energy, grad
 
@@ -152,8 +159,19 @@ def energy_grad_host(tet_sp: TetSpheres, x_host: torch.Tensor, c1: float, c2: fl
     _capi.check(rc, tet_sp._h, "tet_spheres_ext.energy_grad_host")
 
 
+#: bumped by tssplat_b200.optimizer.AdamUniform.step: parameters updated through ``p.data`` do not bump
+#: ``p._version``, so the fused-gradient cache keys on this counter too
+_mutation_epoch = 0
+
+
+def note_parameters_changed() -> None:
+    """Tell the fused-gradient cache that vertex positions were modified in place behind autograd's back."""
+    global _mutation_epoch
+    _mutation_epoch += 1
+
+
 def _key(x: torch.Tensor, c1, c2, order):
-    return (x.data_ptr(), x._version, tuple(x.shape), float(c1), float(c2), int(order))
+    return (x.data_ptr(), x._version, _mutation_epoch, float(c1), float(c2), int(order))
 
 
 def forward(vertexPositions: torch.Tensor, tet_sp: TetSpheres, c1: float, c2: float, order: int) -> torch.Tensor:
@@ -170,24 +188,28 @@ def forward(vertexPositions: torch.Tensor, tet_sp: TetSpheres, c1: float, c2: fl
 
 
 def backward(gradH, vertexPositions: torch.Tensor, tet_sp: TetSpheres, c1: float, c2: float, order: int) -> torch.Tensor:
-    """``gradH * dE/dx`` as a fresh [n,3] fp32 tensor on ``x``'s device
-    (``tet_spheres.cpp:213-216``, ``tet_spheres_cuda.cu:197-263``)."""
-    shape = tuple(vertexPositions.shape)
-    if tet_sp._cache_grad is not None and tet_sp._cache_key == _key(vertexPositions, c1, c2, order):
-        g = tet_sp._cache_grad
-        out = torch.empty_like(g)
-        gh_val, gh_ptr, keep = 1.0, None, None
+    """``gradH * dE/dx`` as a fresh tensor of ``x``'s shape on ``x``'s device
+    (``tet_spheres.cpp:213-216``, ``tet_spheres_cuda.cu:197-263``).  Uses the gradient the fused forward
+    launch already produced when ``x`` has not changed since (single use: a second backward recomputes)."""
+    shape = vertexPositions.shape
+    g = tet_sp._cache_grad
+    if g is not None and tet_sp._cache_key == _key(vertexPositions, c1, c2, order):
+        tet_sp._cache_key, tet_sp._cache_grad = None, None            # single use
         if isinstance(gradH, torch.Tensor) and gradH.is_cuda:
-            keep = gradH.detach().to(device=g.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
-            gh_ptr = keep.data_ptr()
+            keep = gradH if (gradH.dtype == torch.float32 and gradH.device == g.device) else gradH.detach().to(device=g.device, dtype=torch.float32)
+            rc = _capi.lib.tsb_scale(g.data_ptr(), g.numel(), 1.0, keep.data_ptr(), g.data_ptr(), _stream_ptr(g.device))
+            if rc:
+                _capi.check(rc, None, "tet_spheres_ext.backward")
         else:
-            gh_val = float(gradH)
-        rc = _capi.lib.tsb_scale(g.data_ptr(), g.numel(), gh_val, gh_ptr, out.data_ptr(), _stream_ptr(g.device))
-        _capi.check(rc, None, "tet_spheres_ext.backward")
-        del keep
+            gh = float(gradH)
+            if gh != 1.0:
+                rc = _capi.lib.tsb_scale(g.data_ptr(), g.numel(), gh, None, g.data_ptr(), _stream_ptr(g.device))
+                if rc:
+                    _capi.check(rc, None, "tet_spheres_ext.backward")
+        out = g
     else:
         _, out = tet_sp.energy_grad(vertexPositions, c1, c2, order, gradH, want_grad=True)
-    return out.reshape(shape) if len(shape) == 2 else out
+    return out.reshape(shape)
 
 
 def random_x(tet_sp: TetSpheres) -> torch.Tensor:
