@@ -129,6 +129,24 @@ int tsb_adam_uniform_step(float *p_dev, const float *grad_dev, float *g1_dev, fl
                           int64_t count, double lr, double beta1, double beta2, int32_t step,
                           double grad_limit, float *work_dev, void *stream);
 
+/* ---- "Next" row (f)2: surface gather + vertex-normal splat ------------------------------------------------
+ * Replaces `tet_v[surface_vid]` (geometry/tetmesh_geometry.py:33) and `_compute_vertex_normal`
+ * (geometry/tetmesh_geometry.py:39-66) and their autograd backward.  surface_vid: host int32 [nsv] tet-mesh
+ * vertex of each surface vertex (unique); surface_f: host int32 [3*nsf] triangles over surface-vertex ids.
+ * One handle may serve one stream at a time (it owns a backward scratch array). */
+typedef struct tsb_surface_s *tsb_surface_t;
+int tsb_surface_create(const int32_t *surface_vid, int32_t nsv, const int32_t *surface_f, int32_t nsf,
+                       int32_t n_tet_vertices, int device, tsb_surface_t *out);
+void tsb_surface_destroy(tsb_surface_t s);
+const char *tsb_surface_last_error(tsb_surface_t s);
+/* v_pos_dev / v_nrm_dev: device float32 [3*nsv]; either may be NULL.  Normals: sum of cross(v1-v0, v2-v0) over the
+ * incident faces in fixed order, (0,0,1) where |n|^2 <= 1e-20, then n / max(|n|, 1e-12). */
+int tsb_surface_forward(tsb_surface_t s, const float *tet_v_dev, float *v_pos_dev, float *v_nrm_dev, void *stream);
+/* grad_tet_v_dev: device float32 [3*n_tet_vertices], fully overwritten (zero for non-surface vertices);
+ * grad_v_pos_dev / grad_v_nrm_dev: upstream gradients [3*nsv], either may be NULL. */
+int tsb_surface_backward(tsb_surface_t s, const float *tet_v_dev, const float *grad_v_pos_dev,
+                         const float *grad_v_nrm_dev, float *grad_tet_v_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,23 @@ def main():
         out[name + "/surface_vid"] = sv.astype(np.int64)
         out[name + "/surface_f"] = sf.astype(np.int64)
 
+    # vertex normals by EXECUTING the reference's own function body (geometry/tetmesh_geometry.py:39-66; the module
+    # itself cannot be imported: it pulls in pypgo/trimesh at import time)
+    import ast
+    import types
+    import torch.nn.functional as F_
+    src = open(os.path.join(REF, "geometry/tetmesh_geometry.py")).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TetMeshGeometryForwardData")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_compute_vertex_normal")
+    ns = {"torch": torch, "F": F_, "dot": lambda a, b: torch.sum(a * b, -1, keepdim=True)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref:_compute_vertex_normal", "exec"), ns)
+    for name, (v32, t) in meshes.items():
+        sv, sf = out[name + "/surface_vid"], out[name + "/surface_f"]
+        x = torch.from_numpy(out[name + "/inverted/x"])
+        obj = types.SimpleNamespace(v_pos=x[torch.from_numpy(sv)], t_pos_idx=torch.from_numpy(sf))   # tetmesh_geometry.py:33
+        out[name + "/v_nrm"] = ns["_compute_vertex_normal"](obj).numpy()
+
     # AdamUniform trajectory (CPU float32 torch, exactly the reference class)
     torch.manual_seed(0)
     n = 600

@@ -393,3 +393,41 @@ def test_adam_uniform_matches_reference_class(ext):
     st = opt.state[p]
     assert torch.allclose(st["g1"], torch.from_numpy(fix["adam/g1"]).cuda(), rtol=1e-5, atol=1e-7)
     assert torch.allclose(st["g2"], torch.from_numpy(fix["adam/g2"]).cuda(), rtol=1e-5, atol=1e-9)
+
+
+def test_surface_gather_and_vertex_normals(ext):
+    """tssplat_b200.surface (tsb_surface_*): forward against normals produced by the reference's own
+    _compute_vertex_normal body (fixture), forward + backward against the fp64 torch restatement."""
+    from oracle.surface_normals import vertex_normals
+    from tssplat_b200.mesh import surface_vf
+    from tssplat_b200.surface import SurfaceForwardData, SurfaceNormals
+    fix = np.load(os.path.join(GOLDEN, "ref_fixtures.npz"))
+    d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
+    pk = make_pack(3, 1024, seed=1)
+    for name, t in {"a_veg": d["tets"], "pack3x1024": pk.tets}.items():
+        sv, sf = surface_vf(t)
+        x_np = fix[name + "/inverted/x"]
+        surf = SurfaceNormals(sv, sf, len(x_np))
+        tet_v = torch.nn.Parameter(torch.from_numpy(x_np).cuda())
+        v_pos, v_nrm = surf(tet_v)
+        assert torch.equal(v_pos.detach().cpu(), torch.from_numpy(x_np)[torch.from_numpy(sv)])
+        assert np.abs(v_nrm.detach().cpu().numpy() - fix[name + "/v_nrm"]).max() < 2e-6
+        # backward: a generic scalar of both outputs
+        torch.manual_seed(3)
+        wp, wn = torch.randn(len(sv), 3), torch.randn(len(sv), 3)
+        (v_pos * wp.cuda()).sum().add((v_nrm * wn.cuda()).sum()).backward()
+        x64 = torch.from_numpy(x_np).double().requires_grad_(True)
+        p64, n64 = vertex_normals(x64, torch.from_numpy(sv), torch.from_numpy(sf))
+        ((p64 * wp.double()).sum() + (n64 * wn.double()).sum()).backward()
+        g, go = tet_v.grad.cpu().double(), x64.grad
+        assert float((g - go).norm()) <= 1e-5 * float(go.norm())
+        assert torch.all(g[np.setdiff1d(np.arange(len(x_np)), sv)] == 0)               # interior vertices: no gradient
+        v2, n2 = surf.forward(tet_v)
+        assert torch.equal(n2, v_nrm.detach())                                          # bitwise repeatable
+        fd = SurfaceForwardData(tet_v, surf, torch.from_numpy(sf).cuda())
+        assert torch.equal(fd._compute_vertex_normal().detach(), n2) and fd.t_pos_idx.shape == (len(sf), 3)
+    # degenerate fallback: a face of zero area gives (0, 0, 1)
+    sv0 = np.array([0, 1, 2], dtype=np.int32)
+    flat = SurfaceNormals(sv0, np.array([[0, 1, 2]], dtype=np.int32), 3)
+    _, n0 = flat.forward(torch.zeros(3, 3, device="cuda"))
+    assert torch.equal(n0.cpu(), torch.tensor([[0.0, 0.0, 1.0]] * 3))

@@ -176,6 +176,34 @@ def test_veg_round_trip(tmp_path):
         assert np.array_equal(ta, d["tets"]) and np.array_equal(va, d["verts"])
 
 
+def test_surface_extraction_matches_reference_get_surface_vf():
+    """tssplat_b200.mesh.surface_vf against fixtures produced by the reference's own get_surface_vf
+    (geometry/mesh_utils.py:5-35, imported by tests/golden/make_ref_fixtures.py): identical vertex list,
+    identical triangles in identical order and orientation."""
+    from tssplat_b200.mesh import surface_vf
+    fix = np.load(os.path.join(GOLDEN, "ref_fixtures.npz"))
+    d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
+    pk = make_pack(3, 1024, seed=1)
+    for name, t in {"a_veg": d["tets"], "pack3x1024": pk.tets}.items():
+        sv, sf = surface_vf(t)
+        assert np.array_equal(sv, fix[name + "/surface_vid"]) and np.array_equal(sf, fix[name + "/surface_f"])
+    sv, sf = surface_vf(d["tets"])
+    assert len(sv) == 973 and len(sf) == 1942                      # SURVEY 8c: a.veg surface
+
+
+def test_npy_sphere_export_round_trip(tmp_path):
+    from tssplat_b200.mesh import load_npy_spheres, save_npy_spheres
+    pk = make_pack(3, 256, seed=12)
+    files = save_npy_spheres(pk, str(tmp_path), "final")
+    assert len(files) == 2 + 2 * 3
+    e1 = np.load(str(tmp_path / "final_sp1_elem.npy"))
+    assert e1.min() == 0 and e1.max() == pk.vert_offsets[2] - pk.vert_offsets[1] - 1     # sphere-local indices
+    back = load_npy_spheres(str(tmp_path), "final")
+    assert np.array_equal(back.verts, pk.verts) and np.array_equal(back.tets, pk.tets)
+    assert np.array_equal(back.vert_offsets, pk.vert_offsets)
+    assert np.array_equal(np.load(str(tmp_path / "final_vtx.npy")), pk.verts)
+
+
 def test_synthetic_pack_properties():
     from oracle.tet_energy_oracle import face_adjacency
     from tssplat_b200.mesh import _signed_volumes

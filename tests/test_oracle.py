@@ -214,3 +214,19 @@ def test_oracle_barrier_matches_reference_F(aveg, ref_fix):
                 _, terms, _ = o2.energy_grad(x, 1.0, 1.0, order, want_grad=False)
                 assert float(bar) == pytest.approx(want, rel=1e-9, abs=1e-300)
                 assert terms[1] == pytest.approx(want, rel=1e-9, abs=1e-300)
+
+
+def test_surface_normal_restatement_matches_reference_body(aveg, ref_fix):
+    """oracle/surface_normals.py against normals produced by executing the reference's own
+    _compute_vertex_normal body (geometry/tetmesh_geometry.py:39-66) -- fixture v_nrm."""
+    import torch
+    from oracle.surface_normals import vertex_normals
+    for name in ("a_veg", "pack3x1024"):
+        sv = torch.from_numpy(ref_fix[name + "/surface_vid"])
+        sf = torch.from_numpy(ref_fix[name + "/surface_f"])
+        x = torch.from_numpy(ref_fix[name + "/inverted/x"])
+        v_pos, v_nrm = vertex_normals(x, sv, sf)
+        assert torch.equal(v_pos, x[sv])
+        assert np.abs(v_nrm.numpy() - ref_fix[name + "/v_nrm"]).max() < 2e-6        # fp32 summation order
+        _, n64 = vertex_normals(x.double(), sv, sf)
+        assert np.abs(n64.numpy() - ref_fix[name + "/v_nrm"]).max() < 2e-6

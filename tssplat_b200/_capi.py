@@ -19,6 +19,7 @@ TSB_OK, TSB_E_INVALID, TSB_E_MESH, TSB_E_CUDA, TSB_E_NOMEM = 0, -1, -2, -3, -4
 EXPORTED_SYMBOLS = (
     "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_energy_grad_host", "tsb_scale",
     "tsb_grad_limit", "tsb_adam_uniform_step",
+    "tsb_surface_create", "tsb_surface_destroy", "tsb_surface_last_error", "tsb_surface_forward", "tsb_surface_backward",
 )
 
 
@@ -65,6 +66,16 @@ def _load() -> C.CDLL:
     lib.tsb_grad_limit.argtypes = [vp, i64, f32, f32, vp, vp]
     lib.tsb_adam_uniform_step.restype = C.c_int
     lib.tsb_adam_uniform_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, i32, C.c_double, vp, vp]
+    lib.tsb_surface_create.restype = C.c_int
+    lib.tsb_surface_create.argtypes = [vp, i32, vp, i32, i32, C.c_int, C.POINTER(vp)]
+    lib.tsb_surface_destroy.restype = None
+    lib.tsb_surface_destroy.argtypes = [vp]
+    lib.tsb_surface_last_error.restype = C.c_char_p
+    lib.tsb_surface_last_error.argtypes = [vp]
+    lib.tsb_surface_forward.restype = C.c_int
+    lib.tsb_surface_forward.argtypes = [vp, vp, vp, vp, vp]
+    lib.tsb_surface_backward.restype = C.c_int
+    lib.tsb_surface_backward.argtypes = [vp, vp, vp, vp, vp, vp]
     return lib
 
 

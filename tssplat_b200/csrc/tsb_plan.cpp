@@ -723,13 +723,16 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   P.wseg.assign(size_t(NS) * NW * 2, 0);
   P.wdesc.assign(size_t(G) * NW * 2, 0);
   std::vector<std::vector<uint8_t>> wstream(size_t(G) * NW);
+  const int TPC = GLOBAL ? 32 : 64;                        // tets per tet cell
+  const double CTC = double(cfg.tetcell_cost) * (GLOBAL ? 0.6 : 1.0);
+  struct EmitStats { int64_t nnz_padded = 0, n_cells = 0, n_rb = 0, n_tetcells = 0, gwf[2] = {0, 0}, twf[2] = {0, 0}; int rc = TSB_OK; std::string err; };
+  // CTAs are independent: emit them on all host threads (each thread owns a contiguous range of CTAs)
+  auto emit_ctas = [&](int b_begin, int b_end, EmitStats &ES) {
   std::vector<RowRef> rows;
   std::vector<int> rb_of_warp[kMaxWarps];
   LaneSlots lane_slots;
-  const int TPC = GLOBAL ? 32 : 64;                        // tets per tet cell
-  const double CTC = double(cfg.tetcell_cost) * (GLOBAL ? 0.6 : 1.0);
   double load[kMaxWarps] = {0};
-  for (int b = 0; b < G; ++b) {
+  for (int b = b_begin; b < b_end; ++b) {
     for (int s = P.cta_seg[2 * size_t(b)]; s < P.cta_seg[2 * size_t(b) + 1]; ++s) {
       const Seg &g = segs[s];
       const Comp &C = comps[g.comp];
@@ -740,7 +743,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       const bool whole = P.segs[s].whole != 0;
       const int ubase_bytes = GLOBAL ? 0 : (whole ? 0 : (li & 1) * 2 * P.vh * 16);
       const int xbase_bytes = GLOBAL ? 0 : ubase_bytes + (whole ? C.npos : P.vh) * 16;
-      if (!GLOBAL && xbase_bytes + C.npos * 16 > 65536) { err = "internal: staging offsets exceed 16 bits"; return TSB_E_INVALID; }
+      if (!GLOBAL && xbase_bytes + C.npos * 16 > 65536) { ES.err = "internal: staging offsets exceed 16 bits"; ES.rc = TSB_E_INVALID; return; }
       rows.clear();
       for (int r = g.r0; r < g.r1; ++r) rows.push_back(RowRef{r, C.rptr[r + 1] - C.rptr[r]});
       std::stable_sort(rows.begin(), rows.end(), [](const RowRef &a, const RowRef &c) { return a.len > c.len; });
@@ -762,7 +765,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
         while (i < rows.size()) {
           int L = 1;
           while (L < 4 && rb_len4(rows.data() + i, 1, L) > (L < cfg.max_lanes_per_row ? rb_cap : 62)) L *= 2;
-          if (rb_len4(rows.data() + i, 1, L) > 62) { err = "a vertex has more than 980 operator neighbours"; return TSB_E_MESH; }
+          if (rb_len4(rows.data() + i, 1, L) > 62) { ES.err = "a vertex has more than 980 operator neighbours"; ES.rc = TSB_E_MESH; return; }
           const int nr = int(std::min<size_t>(size_t(32 / L), rows.size() - i));
           rbs.push_back(RB{int(i), nr, L, rb_len4(rows.data() + i, nr, L)});
           i += nr;
@@ -795,23 +798,42 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
         for (int k : rb_of_warp[w]) {
           const RB &rb = rbs[k];
           const int len4 = GLOBAL ? emit_rb<uint32_t>(st, C, rows.data() + rb.first, rb.nrows, rb.L, gid, 0, lane_slots, nullptr)
-                                  : emit_rb<uint16_t>(st, C, rows.data() + rb.first, rb.nrows, rb.L, nullptr, ubase_bytes, lane_slots, P.gather_wavefronts);
-          P.nnz_padded += int64_t(len4) * 4 * 32;
-          P.n_cells += len4;
+                                  : emit_rb<uint16_t>(st, C, rows.data() + rb.first, rb.nrows, rb.L, nullptr, ubase_bytes, lane_slots, ES.gwf);
+          ES.nnz_padded += int64_t(len4) * 4 * 32;
+          ES.n_cells += len4;
         }
         for (int k = 0; k < tc_cnt[w]; ++k) {
           const int nt = std::min(TPC, g.t1 - tnext);
           if (GLOBAL) emit_tc<uint32_t>(st, M, C, tnext, nt, 0, nullptr);
-          else emit_tc<uint16_t>(st, M, C, tnext, nt, xbase_bytes, P.tet_wavefronts);
+          else emit_tc<uint16_t>(st, M, C, tnext, nt, xbase_bytes, ES.twf);
           tnext += nt;
         }
-        if (rb_of_warp[w].size() > 0xFFFF || tc_cnt[w] > 0xFFFF) { err = "segment too large for the stream descriptors"; return TSB_E_INVALID; }
+        if (rb_of_warp[w].size() > 0xFFFF || tc_cnt[w] > 0xFFFF) { ES.err = "segment too large for the stream descriptors"; ES.rc = TSB_E_INVALID; return; }
         P.wseg[(size_t(s) * NW + w) * 2] = uint16_t(rb_of_warp[w].size());
         P.wseg[(size_t(s) * NW + w) * 2 + 1] = uint16_t(tc_cnt[w]);
       }
-      P.n_rb += nrb;
-      P.n_tetcells += ntc;
-      P.n_cells += ntc;
+      ES.n_rb += nrb;
+      ES.n_tetcells += ntc;
+      ES.n_cells += ntc;
+    }
+  }
+  };
+  {
+    int nth = cfg.threads > 0 ? cfg.threads : int(std::thread::hardware_concurrency());
+    nth = std::max(1, std::min({nth, 32, G}));
+    std::vector<EmitStats> stats(nth);
+    std::vector<std::thread> th;
+    for (int i = 0; i < nth; ++i) {
+      const int b0 = int(int64_t(G) * i / nth), b1 = int(int64_t(G) * (i + 1) / nth);
+      if (nth == 1) emit_ctas(b0, b1, stats[i]);
+      else th.emplace_back([&, b0, b1, i]() { emit_ctas(b0, b1, stats[i]); });
+    }
+    for (auto &t : th) t.join();
+    for (const EmitStats &e : stats) {
+      if (e.rc != TSB_OK) { err = e.err; return e.rc; }
+      P.nnz_padded += e.nnz_padded; P.n_cells += e.n_cells; P.n_rb += e.n_rb; P.n_tetcells += e.n_tetcells;
+      P.gather_wavefronts[0] += e.gwf[0]; P.gather_wavefronts[1] += e.gwf[1];
+      P.tet_wavefronts[0] += e.twf[0]; P.tet_wavefronts[1] += e.twf[1];
     }
   }
   size_t total = 0;

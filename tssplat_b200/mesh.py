@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 __all__ = ["TetPack", "load_veg", "save_veg", "make_tet_sphere", "make_pack", "concat_spheres",
-           "perturb", "mean_edge_length", "connected_components"]
+           "perturb", "mean_edge_length", "connected_components", "surface_vf", "save_npy_spheres",
+           "load_npy_spheres"]
 
 _EDGES = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]])
 
@@ -233,3 +234,71 @@ def connected_components(n: int, tets: np.ndarray) -> np.ndarray:
     np.minimum.at(first, lab, np.arange(n))
     rank = np.argsort(np.argsort(first))
     return rank[lab]
+
+
+def surface_vf(tets: np.ndarray):
+    """Surface of a tet mesh without pypgo: (surface_vertices, surface_triangles).
+
+    Same outputs, in the same order and with the same orientation, as the reference's
+    ``get_surface_vf`` (``geometry/mesh_utils.py:5-35``): the faces that belong to exactly one tet, listed
+    in lexicographic order of their sorted vertex triple, each written in the orientation its tet gives it
+    (face k opposite local vertex k: (1,2,3), (0,3,2), (0,1,3), (0,2,1)) and re-indexed into the sorted
+    list of surface vertex ids.  ``reset()`` / ``permute_surface_v()`` of the geometry re-run this
+    (``geometry/tetmesh_geometry.py:164-170,369-371``).
+    """
+    tets = np.asarray(tets, dtype=np.int64).reshape(-1, 4)
+    T = len(tets)
+    corner = np.array([[1, 2, 3], [0, 3, 2], [0, 1, 3], [0, 2, 1]])
+    oriented = tets[:, corner].transpose(1, 0, 2).reshape(4 * T, 3)      # block k = faces opposite vertex k
+    key = np.sort(oriented, axis=1)
+    order = np.lexsort((np.arange(4 * T), key[:, 2], key[:, 1], key[:, 0]))   # ties: first occurrence first
+    ks = key[order]
+    new = np.ones(4 * T, dtype=bool)
+    new[1:] = np.any(ks[1:] != ks[:-1], axis=1)
+    start = np.flatnonzero(new)
+    count = np.diff(np.append(start, 4 * T))
+    once = start[count == 1]
+    faces = oriented[order[once]]
+    verts = np.unique(faces)
+    return verts, np.searchsorted(verts, faces)
+
+
+def save_npy_spheres(pack: "TetPack", path: str, filename: str, verts: Optional[np.ndarray] = None) -> List[str]:
+    """The reference's array export without pypgo: ``<filename>_vtx.npy`` / ``_elem.npy`` of the whole mesh
+    (``geometry/tetrahedron_mesh.py:82-91``) and, per sphere i, ``<filename>_sp{i}_vtx.npy`` (its vertices) and
+    ``<filename>_sp{i}_elem.npy`` (its tets with sphere-local indices) as
+    ``geometry/tetmesh_geometry.py:373-382`` writes them.  ``verts`` overrides the positions (e.g. the optimised
+    ``tet_v``).  Returns the written paths."""
+    import os
+    os.makedirs(path, exist_ok=True)
+    V = pack.verts if verts is None else np.asarray(verts).reshape(pack.verts.shape)
+    out = []
+
+    def put(name, arr):
+        f = os.path.join(path, filename + name)
+        np.save(f, arr)
+        out.append(f)
+    put("_vtx.npy", V)
+    put("_elem.npy", pack.tets)
+    for i in range(pack.num_spheres):
+        v0, v1 = int(pack.vert_offsets[i]), int(pack.vert_offsets[i + 1])
+        t0, t1 = int(pack.tet_offsets[i]), int(pack.tet_offsets[i + 1])
+        put(f"_sp{i}_vtx.npy", V[v0:v1])
+        put(f"_sp{i}_elem.npy", (pack.tets[t0:t1] - v0).astype(np.int32))
+    return out
+
+
+def load_npy_spheres(path: str, filename: str) -> "TetPack":
+    """Read back ``<filename>_sp{i}_vtx.npy`` / ``_sp{i}_elem.npy`` (any number of spheres) into a pack,
+    concatenated the way ``geometry/tetmesh_geometry.py:305-331`` does."""
+    import os
+    spheres = []
+    i = 0
+    while os.path.exists(os.path.join(path, f"{filename}_sp{i}_vtx.npy")):
+        v = np.load(os.path.join(path, f"{filename}_sp{i}_vtx.npy"))
+        t = np.load(os.path.join(path, f"{filename}_sp{i}_elem.npy"))
+        spheres.append((v, np.asarray(t).reshape(-1, 4)))
+        i += 1
+    if not spheres:
+        raise FileNotFoundError(f"no {filename}_sp*_vtx.npy under {path}")
+    return concat_spheres(spheres)
