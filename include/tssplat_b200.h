@@ -40,8 +40,22 @@ typedef struct {
   int32_t force_global;     /* 1: gather u/x from global memory instead of staging components in
                                shared memory (the mode used for components too large to stage)   */
   int32_t tet_cost_x100;    /* load-balance weight of one tet vs one operator entry, x100 (0 = default) */
-  int32_t reserved[3];
+  int32_t enable_amips;     /* 1: also keep the per-tet rest inverses (48 B/tet) so that tsb_energy_grad_ex
+                               may add the AMIPS term; 0 (default): c3 must be 0                    */
+  int32_t reserved[2];
 } tsb_options_t;
+
+/* Energy terms of tsb_energy_grad_ex.  c3 weighs the AMIPS term that BASELINE.json's north_star names:
+ *   sum over tets with det F > 0 of  tr(F^T F) / (3 det(F)^(2/3)) - 1     (conformal AMIPS, Fu et al. 2015)
+ * THE REFERENCE HAS NO SUCH TERM (nothing under /root/reference computes it: SURVEY.md F1), so there is no
+ * reference oracle for it: it is verified against two fp64 restatements, finite differences and its known
+ * answers (0 at rest and under similarity maps), never "against the reference".  Default off. */
+typedef struct {
+  float c1, c2;
+  int32_t order;            /* 2 or 4 */
+  float c3;                 /* AMIPS coefficient; 0 = exactly tsb_energy_grad */
+  int32_t reserved[4];
+} tsb_terms_t;
 
 typedef struct {
   int32_t n;                /* vertices                                                          */
@@ -95,6 +109,13 @@ int tsb_get_info(tsb_handle_t h, tsb_info_t *info);
 int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order,
                     float gradH, const float *gradH_dev, float *energy_out_dev,
                     float *grad_out_dev, void *stream);
+
+/* tsb_energy_grad plus the optional AMIPS term.  energy_out_dev: device float32 [4] = total, smoothness,
+ * barrier, AMIPS (unweighted sums; total = c1*smooth + c2*barrier + c3*amips).  With terms->c3 == 0 the launch
+ * is the very kernel tsb_energy_grad runs.  c3 != 0 needs a handle created with enable_amips = 1; its gradient
+ * is added with red.global.add.f32 for every tet (order-dependent rounding). */
+int tsb_energy_grad_ex(tsb_handle_t h, const float *x_dev, const tsb_terms_t *terms, float gradH,
+                       const float *gradH_dev, float *energy_out_dev, float *grad_out_dev, void *stream);
 
 /* Same computation for callers whose vertex positions live in HOST memory (e.g. a CPU-side
  * optimiser): copies x_host -> device, runs the fused launch, copies energy[3] and grad back,

@@ -168,12 +168,30 @@ static inline void cof3(const real *F, real *C) {
   C[6] = F[1] * F[5] - F[2] * F[4]; C[7] = F[2] * F[3] - F[0] * F[5]; C[8] = F[0] * F[4] - F[1] * F[3];
 }
 
-/* x: float32 [n*3].  terms[0] = 1/2||LF||^2 (unweighted by c1), terms[1] = sum barrier (unweighted).
- * grad: double [n*3] or NULL.  Returns 0. */
+/* x: float32 [n*3].  terms[0] = 1/2||LF||^2 (unweighted by c1), terms[1] = sum barrier (unweighted),
+ * terms[2] = sum AMIPS (only written by tso_energy_grad_ex; unweighted).  grad: double [n*3] or NULL.
+ * AMIPS (c3; no counterpart in the reference): psi = tr(F^T F) / (3 det(F)^(2/3)) - 1 for
+ * det F > 0, else 0;  d psi / dF = 2 / (3 J^(2/3)) * (F - tr / (3 J) * cof F). */
+static int tso_energy_grad_impl(TsoOracle *o, const float *x, double c1, double c2, double c3, int order, double gradH,
+                                double *terms, double *grad, int nthreads);
+
 int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int order, double gradH,
                     double *terms, double *grad, int nthreads) {
+  double t3[3];
+  int rc = tso_energy_grad_impl(o, x, c1, c2, 0.0, order, gradH, t3, grad, nthreads);
+  if (terms) { terms[0] = t3[0]; terms[1] = t3[1]; }
+  return rc;
+}
+
+int tso_energy_grad_ex(TsoOracle *o, const float *x, double c1, double c2, double c3, int order, double gradH,
+                       double *terms3, double *grad, int nthreads) {
+  return tso_energy_grad_impl(o, x, c1, c2, c3, order, gradH, terms3, grad, nthreads);
+}
+
+static int tso_energy_grad_impl(TsoOracle *o, const float *x, double c1, double c2, double c3, int order, double gradH,
+                                double *terms, double *grad, int nthreads) {
   const int nele = o->nele, n = o->n;
-  double sm = 0.0, bar = 0.0;
+  double sm = 0.0, bar = 0.0, ami = 0.0;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -203,7 +221,7 @@ int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int orde
       for (int i = 0; i < 9; i++) { H[i] *= o->w[t]; e += H[i] * H[i]; }
       sm += 0.5 * (double)e;
     }
-#pragma omp for schedule(static) reduction(+ : bar)
+#pragma omp for schedule(static) reduction(+ : bar, ami)
     for (int t = 0; t < nele; t++) {
       /* P = c1 * (L^T H)_t + c2 * D_t ;  (L^T H)_t = deg_t w_t H_t - sum_s w_s H_s */
       real P[9];
@@ -223,6 +241,14 @@ int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int orde
         bar += (double)e;
         cof3(F, C);
         for (int i = 0; i < 9; i++) P[i] += (real)c2 * (-coef) * C[i];
+      } else if (c3 != 0.0 && J > 0) {
+        real tr = 0, C[9];
+        for (int i = 0; i < 9; i++) tr += F[i] * F[i];
+        const double j23 = pow((double)J, 2.0 / 3.0);
+        ami += (double)tr / (3.0 * j23) - 1.0;
+        cof3(F, C);
+        const real a = (real)(2.0 / (3.0 * j23)), b = (real)((double)tr / (3.0 * (double)J));
+        for (int i = 0; i < 9; i++) P[i] += (real)c3 * a * (F[i] - b * C[i]);
       }
       /* dE/dx_k = P a_k,  a_k = row k-1 of B (k=1..3), a_0 = -(a_1+a_2+a_3) */
       const real *B = o->B + 9 * t;
@@ -249,7 +275,7 @@ int tso_energy_grad(TsoOracle *o, const float *x, double c1, double c2, int orde
       }
     }
   }
-  if (terms) { terms[0] = sm; terms[1] = bar; }
+  if (terms) { terms[0] = sm; terms[1] = bar; terms[2] = ami; }
   (void)c2;
   return 0;
 }

@@ -215,6 +215,27 @@ class ReferenceEnergyOracle:
         g = g + self.dtype.type(c2) * (self.G.T @ D.reshape(-1).astype(self.dtype))
         return (self.dtype.type(gradH) * g).reshape(-1, 3)
 
+    # ---- AMIPS (BASELINE.json north_star names it; the reference has NO such term: SURVEY.md F1) ----------
+    # No reference oracle exists for this term.  Definition used by the product (default off, c3 = 0), the
+    # conformal AMIPS energy of the tet-meshing literature (Fu et al. 2015; TetWild's mesh-quality energy):
+    #     psi_t = tr(F_t^T F_t) / (3 det(F_t)^(2/3)) - 1   for det F_t > 0,    0 otherwise
+    # (>= 0, zero exactly for similarity maps; inverted tets are left to the barrier term), summed over tets.
+    def amips_terms(self, x):
+        F = (self.G @ np.asarray(x, dtype=self.dtype).reshape(-1)).reshape(-1, 3, 3)
+        J = _det3(F)
+        ok = J > 0
+        tr = (F * F).sum(axis=(1, 2))
+        psi = np.where(ok, tr / (3.0 * np.where(ok, J, 1.0) ** (2.0 / 3.0)) - 1.0, 0.0)
+        return float(psi.sum()), F, J, ok, tr
+
+    def amips_backward(self, gradH, x, c3: float):
+        _, F, J, ok, tr = self.amips_terms(x)
+        Js = np.where(ok, J, 1.0)
+        P = (2.0 / (3.0 * Js ** (2.0 / 3.0)))[:, None, None] * (F - (tr / (3.0 * Js))[:, None, None] * _cof3(F))
+        P[~ok] = 0
+        g = self.dtype.type(c3) * (self.G.T @ P.reshape(-1).astype(self.dtype))
+        return (self.dtype.type(gradH) * g).reshape(-1, 3)
+
     def inverted_fraction(self, x) -> float:
         F = (self.G @ np.asarray(x, dtype=self.dtype).reshape(-1)).reshape(-1, 3, 3)
         return float(np.mean(_det3(F) < 0))

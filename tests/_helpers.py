@@ -32,6 +32,8 @@ class COracle:
         self.lib.tso_destroy.argtypes = [C.c_void_p]
         self.lib.tso_energy_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                              C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.tso_energy_grad_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                C.c_double, C.c_void_p, C.c_void_p, C.c_int]
         self.rest = np.ascontiguousarray(np.asarray(rest, dtype=np.float32).reshape(-1, 3))
         self.tets = np.ascontiguousarray(np.asarray(tets, dtype=np.int32).reshape(-1, 4))
         self.n, self.nele = len(self.rest), len(self.tets)
@@ -52,6 +54,15 @@ class COracle:
         self.lib.tso_energy_grad(self.h, x.ctypes.data, float(c1), float(c2), int(order), float(gradH),
                                  terms.ctypes.data, g.ctypes.data if want_grad else None, int(nthreads))
         return float(c1) * terms[0] + float(c2) * terms[1], terms, g
+
+    def energy_grad_ex(self, x, c1, c2, c3, order, gradH=1.0, nthreads=0, want_grad=True):
+        """With the AMIPS term (c3): returns (total, terms[3] = smooth/barrier/amips, grad)."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1, 3))
+        terms = np.zeros(3)
+        g = np.zeros((self.n, 3)) if want_grad else None
+        self.lib.tso_energy_grad_ex(self.h, x.ctypes.data, float(c1), float(c2), float(c3), int(order), float(gradH),
+                                    terms.ctypes.data, g.ctypes.data if want_grad else None, int(nthreads))
+        return float(c1) * terms[0] + float(c2) * terms[1] + float(c3) * terms[2], terms, g
 
 
 PLAN_DEBUG_SO = os.path.join(ROOT, "tests", "native", "libtsb_plan_debug.so")

@@ -431,3 +431,30 @@ def test_surface_gather_and_vertex_normals(ext):
     flat = SurfaceNormals(sv0, np.array([[0, 1, 2]], dtype=np.int32), 3)
     _, n0 = flat.forward(torch.zeros(3, 3, device="cuda"))
     assert torch.equal(n0.cpu(), torch.tensor([[0.0, 0.0, 1.0]] * 3))
+
+
+def test_amips_term_default_off(ext):
+    """a15: the AMIPS term BASELINE.json names.  The reference has none, so the checks are the
+    fp64 restatements (oracle/tet_energy_oracle.{py,c}), the known answers and "c3 = 0 changes nothing"."""
+    pack = make_pack(3, 1024, seed=8)
+    v, t = pack.verts, pack.tets
+    sp = ext.TetSpheres(v.reshape(-1), t.reshape(-1), enable_amips=True)
+    plain = ext.TetSpheres(v.reshape(-1), t.reshape(-1))
+    orc = COracle(v, t)
+    for sig, order in ((0.05, 2), (0.2, 4)):
+        x_np = perturb(pack, sigma_rel=sig, seed=4)
+        x = torch.from_numpy(x_np).cuda()
+        e, g = sp.energy_grad(x, 2e-4, 3e-4, order, 0.8, c3=1e-4)
+        eo, terms, go = orc.energy_grad_ex(x_np, 2e-4, 3e-4, 1e-4, order, gradH=0.8)
+        e, g = e.cpu().numpy().astype(np.float64), g.cpu().numpy().astype(np.float64)
+        assert e[3] == pytest.approx(terms[2], rel=2e-5) and e[0] == pytest.approx(eo, rel=2e-5)
+        assert np.linalg.norm(g - go) <= 2e-5 * np.linalg.norm(go)
+        # c3 = 0 on the AMIPS-enabled handle == the plain handle, bit for bit (no inverted tets at sigma 0.05)
+        e0, g0 = sp.energy_grad(x, 2e-4, 3e-4, order, 0.8)
+        e1, g1 = plain.energy_grad(x, 2e-4, 3e-4, order, 0.8)
+        assert torch.equal(e0, e1) and (sig > 0.1 or torch.equal(g0, g1))
+    rest = torch.from_numpy(v).cuda()
+    e, g = sp.energy_grad(rest, 0.0, 0.0, 2, c3=1.0)                       # rest state: minimum, zero gradient
+    assert abs(float(e[3])) < 1e-3 and float(g.abs().max()) < 1e-3
+    with pytest.raises(RuntimeError, match="enable_amips"):
+        plain.energy_grad(rest, 1.0, 1.0, 2, c3=0.5)

@@ -230,3 +230,28 @@ def test_surface_normal_restatement_matches_reference_body(aveg, ref_fix):
         assert np.abs(v_nrm.numpy() - ref_fix[name + "/v_nrm"]).max() < 2e-6        # fp32 summation order
         _, n64 = vertex_normals(x.double(), sv, sf)
         assert np.abs(n64.numpy() - ref_fix[name + "/v_nrm"]).max() < 2e-6
+
+
+def test_amips_restatements_known_answers_and_finite_differences(sphere):
+    """AMIPS has NO reference oracle: it is pinned by its own properties -- zero at rest, invariant
+    under similarity maps, positive otherwise -- by two independent fp64 restatements and by finite differences."""
+    v, t = sphere
+    o1, o2 = ReferenceEnergyOracle(v, t), COracle(v, t)
+    assert abs(o1.amips_terms(v.astype(np.float32))[0]) < 1e-9                       # rest: F = I
+    q, _ = np.linalg.qr(np.random.default_rng(1).normal(size=(3, 3)))
+    q *= np.sign(np.linalg.det(q))
+    sim = (1.7 * v @ q.T + 0.3).astype(np.float32)                                   # similarity map: still 0
+    assert abs(o2.energy_grad_ex(sim, 0.0, 0.0, 1.0, 2)[1][2]) < 1e-4
+    x = perturb(v, t, 0.25, 4)
+    e1 = o1.amips_terms(x)[0]
+    e2, terms, g2 = o2.energy_grad_ex(x, 0.3, 0.2, 0.7, 2, gradH=0.9)
+    assert e1 > 0 and terms[2] == pytest.approx(e1, rel=1e-10)
+    g1 = o1.backward(0.9, x, 0.3, 0.2, 2) + o1.amips_backward(0.9, x, 0.7)
+    assert np.linalg.norm(g1 - g2) <= 1e-9 * np.linalg.norm(g1)
+    rng = np.random.default_rng(7)                                                   # finite differences in fp64
+    d = rng.normal(size=x.shape)
+    x64 = x.astype(np.float64)
+    h = 1e-7
+    ep, em = o1.amips_terms(x64 + h * d)[0], o1.amips_terms(x64 - h * d)[0]
+    g = o1.amips_backward(1.0, x64, 1.0)
+    assert (ep - em) / (2 * h) == pytest.approx(float(np.sum(g * d)), rel=1e-5)

@@ -17,7 +17,7 @@ TSB_OK, TSB_E_INVALID, TSB_E_MESH, TSB_E_CUDA, TSB_E_NOMEM = 0, -1, -2, -3, -4
 
 # every symbol include/tssplat_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = (
-    "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_energy_grad_host", "tsb_scale",
+    "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_energy_grad_ex", "tsb_energy_grad_host", "tsb_scale",
     "tsb_grad_limit", "tsb_adam_uniform_step",
     "tsb_surface_create", "tsb_surface_destroy", "tsb_surface_last_error", "tsb_surface_forward", "tsb_surface_backward",
 )
@@ -25,7 +25,11 @@ EXPORTED_SYMBOLS = (
 
 class tsb_options_t(C.Structure):
     _fields_ = [("warps_per_cta", C.c_int32), ("laplacian_scale", C.c_int32), ("ring_slots", C.c_int32),
-                ("force_global", C.c_int32), ("tet_cost_x100", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("force_global", C.c_int32), ("tet_cost_x100", C.c_int32), ("enable_amips", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+class tsb_terms_t(C.Structure):
+    _fields_ = [("c1", C.c_float), ("c2", C.c_float), ("order", C.c_int32), ("c3", C.c_float), ("reserved", C.c_int32 * 4)]
 
 
 class tsb_info_t(C.Structure):
@@ -58,6 +62,8 @@ def _load() -> C.CDLL:
     lib.tsb_get_info.argtypes = [vp, C.POINTER(tsb_info_t)]
     lib.tsb_energy_grad.restype = C.c_int
     lib.tsb_energy_grad.argtypes = [vp, vp, f32, f32, i32, f32, vp, vp, vp, vp]
+    lib.tsb_energy_grad_ex.restype = C.c_int
+    lib.tsb_energy_grad_ex.argtypes = [vp, vp, C.POINTER(tsb_terms_t), f32, vp, vp, vp, vp]
     lib.tsb_energy_grad_host.restype = C.c_int
     lib.tsb_energy_grad_host.argtypes = [vp, vp, f32, f32, i32, f32, vp, vp, vp]
     lib.tsb_scale.restype = C.c_int

@@ -20,6 +20,7 @@ struct tsb_handle_s {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   unsigned host_calls = 0;
+  bool amips = false;
   tsb_info_t info{};
   std::vector<void *> allocs;
   std::string err;
@@ -109,6 +110,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     if (opt->tet_cost_x100 > 0) tet_cost_x100 = opt->tet_cost_x100;
     pc.laplacian_scale = opt->laplacian_scale ? 1 : 0;
     pc.force_global = opt->force_global ? 1 : 0;
+    pc.enable_amips = opt->enable_amips ? 1 : 0;
   }
   if (env_int("TSSPLAT_B200_FORCE_GLOBAL", 0)) pc.force_global = 1;
   pc.max_lanes_per_row = std::max(1, std::min(4, env_int("TSSPLAT_B200_LANES_PER_ROW", pc.max_lanes_per_row)));
@@ -146,7 +148,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
     if (global_mode) while (ch.ring > 2 && tsb::energy_smem_bytes(nw, ch.ring, cpc, 0, true) > smem_optin) --ch.ring;
     ch.smem = tsb::energy_smem_bytes(nw, ch.ring, cpc, global_mode ? 0 : area_verts, global_mode);
     int ctas = 0;
-    cudaError_t e = tsb::energy_occupancy(nw, ch.smem, global_mode, &ctas);
+    cudaError_t e = tsb::energy_occupancy(nw, ch.smem, global_mode, pc.enable_amips != 0, &ctas);
     if (e != cudaSuccess || ctas < 1) {
       cb_err = std::string("kernel does not fit the device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "occupancy 0");
       return 0;
@@ -189,9 +191,15 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   TSB_TRY(upload(h, plan.pos16.data(), plan.pos16.size(), &kp.pos16, 2));
   TSB_TRY(upload(h, plan.pos_gid.data(), plan.pos_gid.size(), &kp.pos_gid, 1));
   TSB_TRY(upload(h, plan.orphans.data(), plan.orphans.size(), &kp.orphans, 1));
+  if (pc.enable_amips) {
+    const float *bt = nullptr;
+    TSB_TRY(upload(h, plan.Bt.data(), plan.Bt.size(), &bt, 4));
+    kp.Bt = reinterpret_cast<const float4 *>(bt);
+    TSB_TRY(upload(h, plan.wtc0.data(), plan.wtc0.size(), &kp.wtc0, 1));
+  }
   TSB_TRY(alloc_zero(h, size_t(plan.n_components), &kp.done));
   {
-    std::vector<unsigned long long> init(size_t(plan.grid) * 2, tsb::kEnergySentinel);
+    std::vector<unsigned long long> init(size_t(plan.grid) * 4, tsb::kEnergySentinel);
     const unsigned long long *ce = nullptr;
     TSB_TRY(upload(h, init.data(), init.size(), &ce, 2));
     kp.cta_energy = reinterpret_cast<double *>(const_cast<unsigned long long *>(ce));
@@ -211,7 +219,8 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   kp.ring_bytes = tsb::energy_ring_bytes(ch.ring, cpc, plan.mode_global != 0);
   kp.cells_per_chunk = cpc;
   kp.stage_bytes = plan.mode_global ? 0 : plan.area_verts * 32;
-  h->lc = tsb::LaunchConfig{nw, plan.grid, ch.smem, plan.mode_global};
+  h->lc = tsb::LaunchConfig{nw, plan.grid, ch.smem, plan.mode_global, 0};
+  h->amips = pc.enable_amips != 0;
 
   tsb_info_t &I = h->info;
   I.n = plan.n; I.nele = plan.nele; I.n_components = plan.n_components; I.grid = plan.grid;
@@ -247,20 +256,35 @@ int tsb_get_info(tsb_handle_t h, tsb_info_t *info) {
   return TSB_OK;
 }
 
-int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order, float gradH,
-                    const float *gradH_dev, float *energy_out_dev, float *grad_out_dev, void *stream) {
+static int energy_grad_impl(tsb_handle_t h, const float *x_dev, float c1, float c2, float c3, int32_t order, float gradH,
+                            const float *gradH_dev, float *energy_out_dev, int energy4, float *grad_out_dev, void *stream) {
   if (!h) return TSB_E_INVALID;
   if (!x_dev || !energy_out_dev) return fail(h, TSB_E_INVALID, "x_dev and energy_out_dev must be non-null");
   if (order != 2 && order != 4)
     return fail(h, TSB_E_INVALID, "order must be 2 or 4 (the reference yields zeros for anything else: tet_spheres_cuda.cu:57-63)");
+  if (c3 != 0.f && !h->amips) return fail(h, TSB_E_INVALID, "c3 != 0 needs a handle created with tsb_options_t.enable_amips = 1");
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(h, TSB_E_CUDA, "cannot select the handle's CUDA device");
   tsb::KParams kp = h->kp;
   kp.x = x_dev; kp.grad = grad_out_dev; kp.energy_out = energy_out_dev; kp.gradH_dev = gradH_dev;
-  kp.c1 = c1; kp.c2 = c2; kp.gradH = gradH; kp.order = order;
-  cudaError_t e = tsb::launch_energy_grad(kp, h->lc, static_cast<cudaStream_t>(stream));
+  kp.c1 = c1; kp.c2 = c2; kp.c3 = c3; kp.gradH = gradH; kp.order = order; kp.energy4 = energy4;
+  tsb::LaunchConfig lc = h->lc;
+  lc.amips = c3 != 0.f ? 1 : 0;          // c3 == 0: the very instantiation tsb_energy_grad always ran
+  cudaError_t e = tsb::launch_energy_grad(kp, lc, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("energy_grad launch: ") + cudaGetErrorString(e));
   return TSB_OK;
+}
+
+int tsb_energy_grad(tsb_handle_t h, const float *x_dev, float c1, float c2, int32_t order, float gradH,
+                    const float *gradH_dev, float *energy_out_dev, float *grad_out_dev, void *stream) {
+  return energy_grad_impl(h, x_dev, c1, c2, 0.f, order, gradH, gradH_dev, energy_out_dev, 0, grad_out_dev, stream);
+}
+
+int tsb_energy_grad_ex(tsb_handle_t h, const float *x_dev, const tsb_terms_t *terms, float gradH, const float *gradH_dev,
+                       float *energy_out_dev, float *grad_out_dev, void *stream) {
+  if (!h) return TSB_E_INVALID;
+  if (!terms) return fail(h, TSB_E_INVALID, "terms is null");
+  return energy_grad_impl(h, x_dev, terms->c1, terms->c2, terms->c3, terms->order, gradH, gradH_dev, energy_out_dev, 1, grad_out_dev, stream);
 }
 
 int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2, int32_t order, float gradH,

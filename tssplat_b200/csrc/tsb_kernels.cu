@@ -89,7 +89,7 @@ __host__ __device__ constexpr int off_rings(int stage_bytes) { return align_up(s
 __host__ __device__ constexpr int off_bars(int stage_bytes, int nw, int ring) { return off_rings(stage_bytes) + nw * ring; }
 __host__ __device__ constexpr int off_red(int stage_bytes, int nw, int ring) { return off_bars(stage_bytes, nw, ring) + nw * kMaxSlots * 8; }
 constexpr int kSegTab = 16;   // segment headers (and per-warp block counts) of a CTA cached in shared memory; beyond that: global
-__host__ __device__ constexpr int off_segtab(int stage_bytes, int nw, int ring) { return align_up(off_red(stage_bytes, nw, ring) + nw * 16, 32); }
+__host__ __device__ constexpr int off_segtab(int stage_bytes, int nw, int ring) { return align_up(off_red(stage_bytes, nw, ring) + nw * 24, 32); }
 __host__ __device__ constexpr int off_wsegtab(int stage_bytes, int nw, int ring) { return off_segtab(stage_bytes, nw, ring) + kSegTab * 32; }
 __host__ __device__ constexpr int smem_total(int stage_bytes, int nw, int ring) { return align_up(off_wsegtab(stage_bytes, nw, ring) + kSegTab * nw * 4, 128); }
 
@@ -151,7 +151,7 @@ struct WarpStream {
   }
 };
 
-template <int NW, int MINB, bool GLOBAL>
+template <int NW, int MINB, bool GLOBAL, bool AMIPS>
 __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParams p) {
   using F = Fmt<GLOBAL>;
   constexpr int NT = NW * 32;
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
   TSB_STAMP(3);
 
   const float gh = p.gradH * (p.gradH_dev ? __ldcg(p.gradH_dev) : 1.f);
-  const float s1 = gh * p.c1, s2 = gh * p.c2;
+  const float s1 = gh * p.c1, s2 = gh * p.c2, s3 = gh * p.c3;
+  const bool amips_on = AMIPS && p.c3 != 0.f && p.Bt != nullptr;
   const bool order2 = p.order == 2;
   float *__restrict__ grad = p.grad;
   if (grad) {   // vertices no tet references: zero gradient
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     }
   }
 
-  double des = 0.0, deb = 0.0;     // per-lane energy partials
+  double des = 0.0, deb = 0.0, dea = 0.0;     // per-lane energy partials (smoothness, barrier, AMIPS)
 
   auto load_x = [&](const SegHdr &h) {      // x of a double-buffered component -> registers
 #pragma unroll
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
 
     // ---- barrier: TPL tets per lane ---------------------------------------------------------------------
     bool waited = false;
+    const int tcell0 = amips_on ? __ldg(&p.wtc0[size_t(s) * NW + warp]) : 0;
     for (int tc = 0; tc < int(wseg.y); ++tc) {
       uint32_t tj[F::TPL][4];
       float tdet[F::TPL];
@@ -432,6 +434,59 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
             atomicAdd(grad + v2, g2x); atomicAdd(grad + v2 + 1, g2y); atomicAdd(grad + v2 + 2, g2z);
             atomicAdd(grad + v3, g3x); atomicAdd(grad + v3 + 1, g3y); atomicAdd(grad + v3 + 2, g3z);
           }
+        } else if (AMIPS && amips_on && J > 0.f) {
+          // AMIPS (default off; no counterpart in the reference -- SURVEY.md F1):  psi = tr(F^T F) / (3 J^(2/3)) - 1,
+          // d psi / dF = 2 / (3 J^(2/3)) (F - tr / (3 J) cof F),  F = Ds B with B = Dm^-1 streamed per tet
+          const int slot = lane * int(F::TPL) + t;
+          const float4 *bp = p.Bt + (size_t(tcell0 + tc) * 3) * (32 * F::TPL) + slot;
+          const float4 b0 = __ldg(bp), b1 = __ldg(bp + 32 * F::TPL), b2 = __ldg(bp + 64 * F::TPL);
+          float Fm[3][3];
+          const float ex[3] = {e1x, e2x, e3x}, ey[3] = {e1y, e2y, e3y}, ez[3] = {e1z, e2z, e3z};
+          const float bb[3][3] = {{b0.x, b0.y, b0.z}, {b1.x, b1.y, b1.z}, {b2.x, b2.y, b2.z}};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            Fm[0][c] = ex[0] * bb[0][c] + ex[1] * bb[1][c] + ex[2] * bb[2][c];
+            Fm[1][c] = ey[0] * bb[0][c] + ey[1] * bb[1][c] + ey[2] * bb[2][c];
+            Fm[2][c] = ez[0] * bb[0][c] + ez[1] * bb[1][c] + ez[2] * bb[2][c];
+          }
+          float tr = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tr = fmaf(Fm[r][c], Fm[r][c], tr);
+          const float cb = cbrtf(J), j23 = cb * cb;
+          dea += double(tr / (3.f * j23) - 1.f);
+          if (grad) {
+            const float a = 2.f / (3.f * j23) * s3, bq = tr / (3.f * J);
+            float Pm[3][3];   // a (F - bq cof F)
+            Pm[0][0] = a * (Fm[0][0] - bq * (Fm[1][1] * Fm[2][2] - Fm[1][2] * Fm[2][1]));
+            Pm[0][1] = a * (Fm[0][1] - bq * (Fm[1][2] * Fm[2][0] - Fm[1][0] * Fm[2][2]));
+            Pm[0][2] = a * (Fm[0][2] - bq * (Fm[1][0] * Fm[2][1] - Fm[1][1] * Fm[2][0]));
+            Pm[1][0] = a * (Fm[1][0] - bq * (Fm[0][2] * Fm[2][1] - Fm[0][1] * Fm[2][2]));
+            Pm[1][1] = a * (Fm[1][1] - bq * (Fm[0][0] * Fm[2][2] - Fm[0][2] * Fm[2][0]));
+            Pm[1][2] = a * (Fm[1][2] - bq * (Fm[0][1] * Fm[2][0] - Fm[0][0] * Fm[2][1]));
+            Pm[2][0] = a * (Fm[2][0] - bq * (Fm[0][1] * Fm[1][2] - Fm[0][2] * Fm[1][1]));
+            Pm[2][1] = a * (Fm[2][1] - bq * (Fm[0][2] * Fm[1][0] - Fm[0][0] * Fm[1][2]));
+            Pm[2][2] = a * (Fm[2][2] - bq * (Fm[0][0] * Fm[1][1] - Fm[0][1] * Fm[1][0]));
+            if (!waited) {
+              const unsigned int need = unsigned(hcur.expected);
+              while (ld_acquire(p.done + hcur.comp) < need) __nanosleep(40);
+              waited = true;
+            }
+            float g0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {       // vertex k+1 pulls with P a_{k+1},  a_{k+1} = row k of B
+              const size_t vk = 3 * gid_x(tj[t][k + 1]);
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const float g = Pm[r][0] * bb[k][0] + Pm[r][1] * bb[k][1] + Pm[r][2] * bb[k][2];
+                atomicAdd(grad + vk + r, g);
+                g0[r] -= g;
+              }
+            }
+            const size_t v0 = 3 * gid_x(tj[t][0]);
+            atomicAdd(grad + v0, g0[0]); atomicAdd(grad + v0 + 1, g0[1]); atomicAdd(grad + v0 + 2, g0[2]);
+          }
         }
       }
     }
@@ -455,37 +510,45 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
   TSB_STAMP(7);
   des = warp_sum(des);
   deb = warp_sum(deb);
-  if (lane == 0) { red[2 * warp] = des; red[2 * warp + 1] = deb; }
+  if (AMIPS) dea = warp_sum(dea);
+  if (lane == 0) { red[3 * warp] = des; red[3 * warp + 1] = deb; red[3 * warp + 2] = dea; }
   __syncthreads();
   TSB_STAMP(8);
   if (tid == 0) {
-    double a = 0.0, b = 0.0;
-    for (int w = 0; w < NW; ++w) { a += red[2 * w]; b += red[2 * w + 1]; }
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int w = 0; w < NW; ++w) { a += red[3 * w]; b += red[3 * w + 1]; c += red[3 * w + 2]; }
     a *= 0.5;
-    // one 16-byte store carries the pair; its arrival IS the "this CTA is done" signal (no fence, no ticket)
+    // two 16-byte stores carry the partials; their arrival IS the "this CTA is done" signal (no fence, no ticket)
     unsigned long long ua = (unsigned long long)__double_as_longlong(a), ub = (unsigned long long)__double_as_longlong(b);
+    unsigned long long uc = (unsigned long long)__double_as_longlong(c);
     if (ua == kSentinel) ua = 0x7FF8000000000000ull;
     if (ub == kSentinel) ub = 0x7FF8000000000000ull;
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 2 * blockIdx.x), "l"(ua), "l"(ub) : "memory");
+    if (uc == kSentinel) uc = 0x7FF8000000000000ull;
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * blockIdx.x), "l"(ua), "l"(ub) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * blockIdx.x + 2), "l"(uc), "l"(0ull) : "memory");
   }
   TSB_STAMP(9);
   if (blockIdx.x == 0 && warp == 0) {
     __syncwarp();
-    double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0, c3sum = 0.0;
     for (int c = lane; c < int(gridDim.x); c += 32) {
-      unsigned long long ua, ub;
+      unsigned long long ua, ub, uc, ud;
       do {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(p.cta_energy + 2 * c) : "memory");
-      } while (ua == kSentinel || ub == kSentinel);
-      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 2 * c), "l"(kSentinel), "l"(kSentinel) : "memory");   // re-arm
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(p.cta_energy + 4 * c) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(uc), "=l"(ud) : "l"(p.cta_energy + 4 * c + 2) : "memory");
+      } while (ua == kSentinel || ub == kSentinel || uc == kSentinel || ud == kSentinel);
+      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c), "l"(kSentinel), "l"(kSentinel) : "memory");   // re-arm
+      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c + 2), "l"(kSentinel), "l"(kSentinel) : "memory");
       a += __longlong_as_double((long long)ua);
       b += __longlong_as_double((long long)ub);
+      c3sum += __longlong_as_double((long long)uc);
     }
-    a = warp_sum(a); b = warp_sum(b);
+    a = warp_sum(a); b = warp_sum(b); c3sum = warp_sum(c3sum);
     if (lane == 0) {
-      p.energy_out[0] = float(double(p.c1) * a + double(p.c2) * b);
+      p.energy_out[0] = float(double(p.c1) * a + double(p.c2) * b + double(p.c3) * c3sum);
       p.energy_out[1] = float(a);
       p.energy_out[2] = float(b);
+      if (p.energy4) p.energy_out[3] = float(c3sum);
     }
     for (int c = lane; c < p.n_components; c += 32) p.done[c] = 0u;   // every CTA has finished: safe to re-arm
   }
@@ -588,7 +651,7 @@ inline int grid_for(int64_t count, int block) {
   return int(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 
-template <int NW, int MINB, bool GLOBAL>
+template <int NW, int MINB, bool GLOBAL, bool AMIPS>
 cudaError_t launch_variant(const KParams &p, const LaunchConfig &lc, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(lc.grid));
@@ -601,14 +664,19 @@ cudaError_t launch_variant(const KParams &p, const LaunchConfig &lc, cudaStream_
   attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, energy_grad_kernel<NW, MINB, GLOBAL>, p);
+  return cudaLaunchKernelEx(&cfg, energy_grad_kernel<NW, MINB, GLOBAL, AMIPS>, p);
 }
 
 template <int NW, int MINB, bool GLOBAL>
-cudaError_t occupancy_variant(int smem_bytes, int *ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+cudaError_t occupancy_variant(int smem_bytes, bool amips, int *ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess && amips) e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) { *ctas_per_sm = 0; cudaGetLastError(); return cudaSuccess; }   // does not fit
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, energy_grad_kernel<NW, MINB, GLOBAL>, NW * 32, size_t(smem_bytes));
+  int a = 0, b = 1 << 30;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, energy_grad_kernel<NW, MINB, GLOBAL, false>, NW * 32, size_t(smem_bytes));
+  if (e == cudaSuccess && amips) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, energy_grad_kernel<NW, MINB, GLOBAL, true>, NW * 32, size_t(smem_bytes));
+  *ctas_per_sm = a < b ? a : b;
+  return e;
 }
 
 }  // namespace
@@ -619,9 +687,9 @@ int energy_smem_bytes(int nw, int ring_slots, int cells_per_chunk, int area_vert
   return smem_total(global ? 0 : area_verts * 32, nw, energy_ring_bytes(ring_slots, cells_per_chunk, global));
 }
 
-cudaError_t energy_occupancy(int nw, int smem_bytes, bool global, int *ctas_per_sm) {
-  if (nw == 16) return global ? occupancy_variant<16, 1, true>(smem_bytes, ctas_per_sm) : occupancy_variant<16, 1, false>(smem_bytes, ctas_per_sm);
-  if (nw == 8) return global ? occupancy_variant<8, 2, true>(smem_bytes, ctas_per_sm) : occupancy_variant<8, 2, false>(smem_bytes, ctas_per_sm);
+cudaError_t energy_occupancy(int nw, int smem_bytes, bool global, bool amips, int *ctas_per_sm) {
+  if (nw == 16) return global ? occupancy_variant<16, 1, true>(smem_bytes, amips, ctas_per_sm) : occupancy_variant<16, 1, false>(smem_bytes, amips, ctas_per_sm);
+  if (nw == 8) return global ? occupancy_variant<8, 2, true>(smem_bytes, amips, ctas_per_sm) : occupancy_variant<8, 2, false>(smem_bytes, amips, ctas_per_sm);
   return cudaErrorInvalidValue;
 }
 
@@ -630,12 +698,12 @@ cudaError_t launch_energy_grad(const KParams &p, const LaunchConfig &lc, cudaStr
     prestage_kernel<<<grid_for(p.n, 256), 256, 0, stream>>>(p.x, p.X4, p.u4g, p.x4g, p.n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (lc.nw == 16) return launch_variant<16, 1, true>(p, lc, stream);
-    if (lc.nw == 8) return launch_variant<8, 2, true>(p, lc, stream);
+    if (lc.nw == 16) return lc.amips ? launch_variant<16, 1, true, true>(p, lc, stream) : launch_variant<16, 1, true, false>(p, lc, stream);
+    if (lc.nw == 8) return lc.amips ? launch_variant<8, 2, true, true>(p, lc, stream) : launch_variant<8, 2, true, false>(p, lc, stream);
     return cudaErrorInvalidValue;
   }
-  if (lc.nw == 16) return launch_variant<16, 1, false>(p, lc, stream);
-  if (lc.nw == 8) return launch_variant<8, 2, false>(p, lc, stream);
+  if (lc.nw == 16) return lc.amips ? launch_variant<16, 1, false, true>(p, lc, stream) : launch_variant<16, 1, false, false>(p, lc, stream);
+  if (lc.nw == 8) return lc.amips ? launch_variant<8, 2, false, true>(p, lc, stream) : launch_variant<8, 2, false, false>(p, lc, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -438,7 +438,7 @@ int emit_rb(std::vector<uint8_t> &s, const Comp &C, const RowRef *rows, int nrow
 
 // Appends one tet cell: STAGED 64 tets (2 per lane), GLOBAL 32 tets.
 template <class IDX>
-void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int nt, int xbase_bytes, int64_t *stat) {
+void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int nt, int xbase_bytes, int64_t *stat, std::vector<float> *Bout) {
   constexpr bool kGlobal = sizeof(IDX) == 4;
   constexpr size_t CELL = kGlobal ? kCellGlobal : kCellStaged;
   constexpr int TPL = kGlobal ? 1 : 2;
@@ -454,6 +454,8 @@ void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int 
                                        {2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},{2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
   uint32_t used[4][2][4];      // [quarter][tet slot][gather] -> residues taken
   std::memset(used, 0, sizeof(used));
+  size_t bo = 0;
+  if (Bout) { bo = Bout->size(); Bout->resize(bo + size_t(3) * 32 * TPL * 4, 0.f); }   // [row][lane*TPL + k] float4
   for (int i = 0; i < nt; ++i) {
     const int l = i / TPL, k = i % TPL;          // lane, tet slot inside the lane
     const int32_t t = C.tets[size_t(t0) + i];
@@ -481,6 +483,9 @@ void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int 
     if (!kGlobal && std::getenv("TSB_EXPERIMENT_NOCONFLICT"))
       for (int c = 0; c < 4; ++c) put<IDX>(s, o + ((size_t(l) * TPL + k) * 4 + c) * sizeof(IDX), IDX(xbase_bytes + (l & 7) * 16));
     put<float>(s, o + DOFF + (size_t(l) * TPL + k) * 4, float(1.0 / det));
+    if (Bout)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) (*Bout)[bo + (size_t(r) * 32 * TPL + size_t(l) * TPL + k) * 4 + c] = float(B[3 * r + c]);
   }
 }
 
@@ -723,6 +728,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   P.wseg.assign(size_t(NS) * NW * 2, 0);
   P.wdesc.assign(size_t(G) * NW * 2, 0);
   std::vector<std::vector<uint8_t>> wstream(size_t(G) * NW);
+  std::vector<std::vector<float>> wB(cfg.enable_amips ? size_t(G) * NW : 0);
   const int TPC = GLOBAL ? 32 : 64;                        // tets per tet cell
   const double CTC = double(cfg.tetcell_cost) * (GLOBAL ? 0.6 : 1.0);
   struct EmitStats { int64_t nnz_padded = 0, n_cells = 0, n_rb = 0, n_tetcells = 0, gwf[2] = {0, 0}, twf[2] = {0, 0}; int rc = TSB_OK; std::string err; };
@@ -804,8 +810,9 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
         }
         for (int k = 0; k < tc_cnt[w]; ++k) {
           const int nt = std::min(TPC, g.t1 - tnext);
-          if (GLOBAL) emit_tc<uint32_t>(st, M, C, tnext, nt, 0, nullptr);
-          else emit_tc<uint16_t>(st, M, C, tnext, nt, xbase_bytes, ES.twf);
+          std::vector<float> *bo = cfg.enable_amips ? &wB[size_t(b) * NW + w] : nullptr;
+          if (GLOBAL) emit_tc<uint32_t>(st, M, C, tnext, nt, 0, nullptr, bo);
+          else emit_tc<uint16_t>(st, M, C, tnext, nt, xbase_bytes, ES.twf, bo);
           tnext += nt;
         }
         if (rb_of_warp[w].size() > 0xFFFF || tc_cnt[w] > 0xFFFF) { ES.err = "segment too large for the stream descriptors"; ES.rc = TSB_E_INVALID; return; }
@@ -835,6 +842,21 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       P.gather_wavefronts[0] += e.gwf[0]; P.gather_wavefronts[1] += e.gwf[1];
       P.tet_wavefronts[0] += e.twf[0]; P.tet_wavefronts[1] += e.twf[1];
     }
+  }
+  if (cfg.enable_amips) {       // rest inverses in (CTA, warp) order + the first tet cell of every (segment, warp)
+    P.wtc0.assign(size_t(NS) * NW, 0);
+    const size_t per_cell = size_t(3) * TPC * 4;
+    size_t cells = 0;
+    for (int b = 0; b < G; ++b)
+      for (int w = 0; w < NW; ++w) {
+        for (int sgi = P.cta_seg[2 * size_t(b)]; sgi < P.cta_seg[2 * size_t(b) + 1]; ++sgi) {
+          P.wtc0[size_t(sgi) * NW + w] = int32_t(cells);
+          cells += P.wseg[(size_t(sgi) * NW + w) * 2 + 1];
+        }
+        const auto &v = wB[size_t(b) * NW + w];
+        P.Bt.insert(P.Bt.end(), v.begin(), v.end());
+      }
+    if (P.Bt.size() != cells * per_cell) { err = "internal: AMIPS rest-inverse blocks out of step with the tet cells"; return TSB_E_INVALID; }
   }
   size_t total = 0;
   for (const auto &st : wstream) total += st.size();

@@ -80,6 +80,7 @@ struct PlanConfig {
   int32_t ring_cells = 12;         // cells one warp's TMA ring holds (decides the latency / streaming regime)
   int32_t rb_cap_div = 2;          // latency regime: a row block is at most ring_cells / rb_cap_div cells
   int32_t threads = 0;          // host threads for the build (0 = hardware concurrency, capped)
+  int32_t enable_amips = 0;     // also emit the per-tet rest inverses (AMIPS term; 48 B per tet)
 };
 
 struct HostPlan {
@@ -110,6 +111,10 @@ struct HostPlan {
   std::vector<uint32_t> wdesc;      // [2*grid*nw] (stream offset / 16, stream bytes)
   std::vector<uint16_t> wseg;       // [2*nsegs*nw] (row blocks, tet cells) of each warp in each segment
   std::vector<int32_t> orphans;     // vertices no tet references (their gradient is zero)
+  // AMIPS only: rest inverses B = Dm^-1 of every streamed tet (in its streamed vertex order), one block of
+  // 3 rows x (tets per cell) float4 per tet cell, and the first tet cell of every (segment, warp)
+  std::vector<float> Bt;
+  std::vector<int32_t> wtc0;
 };
 
 // Returns 0 on success, TSB_E_* otherwise (message in err).

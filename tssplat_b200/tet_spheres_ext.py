@@ -54,7 +54,7 @@ class TetSpheres:
     """
 
     def __init__(self, vertices, elements=None, *, device=None, warps_per_cta: int = 0,
-                 laplacian_scale: int = 0, force_global: bool = False, ring_slots: int = 0):
+                 laplacian_scale: int = 0, force_global: bool = False, ring_slots: int = 0, enable_amips: bool = False):
         self._h = None
         if isinstance(vertices, (str, bytes)) and elements is None:
             v, t = load_veg(vertices if isinstance(vertices, str) else vertices.decode())
@@ -80,7 +80,8 @@ class TetSpheres:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         torch.cuda.init()
         opt = _capi.tsb_options_t(warps_per_cta=int(warps_per_cta), laplacian_scale=int(laplacian_scale),
-                                  ring_slots=int(ring_slots), force_global=int(bool(force_global)))
+                                  ring_slots=int(ring_slots), force_global=int(bool(force_global)),
+                                  enable_amips=int(bool(enable_amips)))
         h = C.c_void_p()
         rc = _capi.lib.tsb_create(vertices.ctypes.data, elements.ctypes.data, vertices.size // 3,
                                   elements.size // 4, C.byref(opt), self.device.index, C.byref(h))
@@ -95,7 +96,7 @@ class TetSpheres:
         self._cache_key = None
         self._cache_grad: Optional[torch.Tensor] = None
         # energies of the last 32 launches (a ring, so a loss tensor stays valid while it is being logged)
-        self._energy_ring = torch.zeros((32, 3), dtype=torch.float32, device=self.device)
+        self._energy_ring = torch.zeros((32, 4), dtype=torch.float32, device=self.device)
         self._ring_i = 0
 
     def __del__(self):
@@ -117,13 +118,14 @@ class TetSpheres:
         return x if x.is_contiguous() else x.contiguous()            # tet_spheres_cuda.cu:124
 
     def energy_grad(self, x: torch.Tensor, c1: float, c2: float, order: int, gradH=1.0,
-                    want_grad: bool = True):
-        """The fused launch.  Returns (energy[3] = total/smooth/barrier on device, grad or None).
+                    want_grad: bool = True, c3: float = 0.0):
+        """The fused launch.  Returns (energy[3] = total/smooth/barrier on device, grad or None); with ``c3``
+        (AMIPS coefficient, handle created with ``enable_amips=True``) the energy has a 4th entry, the AMIPS sum.
         The energy tensor is a slot of a 32-deep ring owned by the handle (no allocation per call)."""
         xc = self._check_x(x)
         i = self._ring_i
         self._ring_i = (i + 1) & 31
-        energy = self._energy_ring[i]
+        energy = self._energy_ring[i] if c3 else self._energy_ring[i, :3]
         grad = torch.empty((self.n, 3), dtype=torch.float32, device=self.device) if want_grad else None
         gh_val, gh_ptr, keep = 1.0, None, None
         if isinstance(gradH, torch.Tensor):
@@ -134,9 +136,14 @@ class TetSpheres:
                 gh_val = float(gradH)
         else:
             gh_val = float(gradH)
-        rc = _capi.lib.tsb_energy_grad(self._h, xc.data_ptr(), float(c1), float(c2), int(order), gh_val,
-                                       gh_ptr, energy.data_ptr(), grad.data_ptr() if want_grad else None,
-                                       _stream_ptr(self.device))
+        if c3:
+            terms = _capi.tsb_terms_t(c1=float(c1), c2=float(c2), order=int(order), c3=float(c3))
+            rc = _capi.lib.tsb_energy_grad_ex(self._h, xc.data_ptr(), C.byref(terms), gh_val, gh_ptr, energy.data_ptr(),
+                                              grad.data_ptr() if want_grad else None, _stream_ptr(self.device))
+        else:
+            rc = _capi.lib.tsb_energy_grad(self._h, xc.data_ptr(), float(c1), float(c2), int(order), gh_val,
+                                           gh_ptr, energy.data_ptr(), grad.data_ptr() if want_grad else None,
+                                           _stream_ptr(self.device))
         if rc:
             _capi.check(rc, self._h, "tet_spheres_ext")
         del keep
