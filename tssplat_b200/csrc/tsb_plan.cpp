@@ -452,36 +452,90 @@ void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int 
   // bank groups in each of its 4 gathers (greedy over the 24 permutations).
   static const uint8_t kPerm[24][4] = {{0,1,2,3},{0,1,3,2},{0,2,1,3},{0,2,3,1},{0,3,1,2},{0,3,2,1},{1,0,2,3},{1,0,3,2},{1,2,0,3},{1,2,3,0},{1,3,0,2},{1,3,2,0},
                                        {2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},{2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
-  uint32_t used[4][2][4];      // [quarter][tet slot][gather] -> residues taken
-  std::memset(used, 0, sizeof(used));
   size_t bo = 0;
   if (Bout) { bo = Bout->size(); Bout->resize(bo + size_t(3) * 32 * TPL * 4, 0.f); }   // [row][lane*TPL + k] float4
+  // choose the vertex order of every tet: min-conflicts over each group of 8 lanes x one tet slot
+  std::vector<uint8_t> perm_of(size_t(nt), 0);
+  if (!kGlobal) {
+    const int ngroups = 4 * TPL;                      // (quarter, slot)
+    for (int gq = 0; gq < ngroups; ++gq) {
+      const int q = gq / TPL, k = gq % TPL;
+      int members[8], nm = 0, pos4[8][4];
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int i = (8 * q + i8) * TPL + k;         // tet index inside the cell: lane * TPL + slot
+        if (i >= nt) continue;
+        const int32_t *v0 = M.tets + 4 * size_t(C.tets[size_t(t0) + i]);
+        for (int c = 0; c < 4; ++c) pos4[nm][c] = C.pos[M.local_of[v0[c]]];
+        members[nm++] = i;
+      }
+      // cost of placing vertex position p in gather c: lanes already reading the same bank group at a
+      // DIFFERENT address (same address = broadcast, free)
+      int cur[8];
+      auto conflicts = [&](int m, int pi) {
+        int hits = 0;
+        for (int c = 0; c < 4; ++c) {
+          const int p = pos4[m][kPerm[pi][c]];
+          for (int o = 0; o < nm; ++o) {
+            if (o == m || cur[o] < 0) continue;
+            const int po = pos4[o][kPerm[cur[o]][c]];
+            hits += ((po & 7) == (p & 7)) && po != p;
+          }
+        }
+        return hits;
+      };
+      for (int m = 0; m < nm; ++m) cur[m] = -1;
+      for (int m = 0; m < nm; ++m) {                  // greedy start
+        int best = 0, best_hits = 1 << 30;
+        for (int pi = 0; pi < 24; ++pi) {
+          const int hits = conflicts(m, pi);
+          if (hits < best_hits) { best_hits = hits; best = pi; if (!hits) break; }
+        }
+        cur[m] = best;
+      }
+      for (int sweep = 0; sweep < 4; ++sweep) {       // local repair
+        bool changed = false;
+        for (int m = 0; m < nm; ++m) {
+          int best = cur[m], best_hits = conflicts(m, cur[m]);
+          if (!best_hits) continue;
+          for (int pi = 0; pi < 24; ++pi) {
+            const int hits = conflicts(m, pi);
+            if (hits < best_hits) { best_hits = hits; best = pi; }
+          }
+          if (best != cur[m]) { cur[m] = best; changed = true; }
+        }
+        if (!changed) break;
+      }
+      if (stat)
+        for (int c = 0; c < 4; ++c) {                  // wavefronts of this gather = max distinct addresses per bank group
+          int worst = 1;
+          for (int r = 0; r < 8; ++r) {
+            int distinct = 0, seen[8];
+            for (int m = 0; m < nm; ++m) {
+              const int p = pos4[m][kPerm[cur[m]][c]];
+              if ((p & 7) != r) continue;
+              bool dup = false;
+              for (int d = 0; d < distinct; ++d) dup |= seen[d] == p;
+              if (!dup) seen[distinct++] = p;
+            }
+            worst = std::max(worst, distinct);
+          }
+          stat[0] += worst; stat[1] += 1;
+        }
+      for (int m = 0; m < nm; ++m) perm_of[members[m]] = uint8_t(cur[m]);
+    }
+  }
   for (int i = 0; i < nt; ++i) {
     const int l = i / TPL, k = i % TPL;          // lane, tet slot inside the lane
     const int32_t t = C.tets[size_t(t0) + i];
     const int32_t *v0 = M.tets + 4 * size_t(t);
-    int32_t v[4] = {v0[0], v0[1], v0[2], v0[3]};
-    if (!kGlobal) {
-      int res[4];
-      for (int c = 0; c < 4; ++c) res[c] = C.pos[M.local_of[v0[c]]] & 7;
-      uint32_t *u = used[l / 8][k];
-      int best = 0, best_hits = 99;
-      for (int pi = 0; pi < 24; ++pi) {
-        int hits = 0;
-        for (int c = 0; c < 4; ++c) hits += (u[c] >> res[kPerm[pi][c]]) & 1u;
-        if (hits < best_hits) { best_hits = hits; best = pi; if (!hits) break; }
-      }
-      for (int c = 0; c < 4; ++c) { v[c] = v0[kPerm[best][c]]; u[c] |= 1u << res[kPerm[best][c]]; }
-      if (stat) { stat[0] += best_hits; stat[1] += 4; }
-    }
+    int32_t v[4];
+    for (int c = 0; c < 4; ++c) v[c] = v0[kPerm[perm_of[i]][c]];
     double Dm[9], B[9], det;
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) Dm[3 * r + c] = double(M.rest[3 * size_t(v[c + 1]) + r]) - double(M.rest[3 * size_t(v[0]) + r]);
     invert3(Dm, B, &det);
     for (int c = 0; c < 4; ++c)
       put<IDX>(s, o + ((size_t(l) * TPL + k) * 4 + c) * sizeof(IDX), kGlobal ? IDX(v[c]) : IDX(xbase_bytes + C.pos[M.local_of[v[c]]] * 16));
-    if (!kGlobal && std::getenv("TSB_EXPERIMENT_NOCONFLICT"))
-      for (int c = 0; c < 4; ++c) put<IDX>(s, o + ((size_t(l) * TPL + k) * 4 + c) * sizeof(IDX), IDX(xbase_bytes + (l & 7) * 16));
     put<float>(s, o + DOFF + (size_t(l) * TPL + k) * 4, float(1.0 / det));
     if (Bout)
       for (int r = 0; r < 3; ++r)

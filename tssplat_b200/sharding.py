@@ -77,17 +77,26 @@ class ShardedEnergy:
         self.tet_sp = ext.TetSpheres(self.local.verts.reshape(-1), self.local.tets.reshape(-1),
                                      device=device, warps_per_cta=warps_per_cta) if self.local.nele else None
         self._work = None
-        self._comm_stream = torch.cuda.Stream(device=self.tet_sp.device) if self.tet_sp is not None else None
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = self.tet_sp.device if self.tet_sp is not None else torch.device(device)
+        self._comm_stream = torch.cuda.Stream(device=self.device)
 
     def energy_grad(self, x_local: torch.Tensor, c1: float, c2: float, order: int, gradH=1.0):
+        """A rank that owns no spheres (more ranks than spheres) still takes part in the collective: it
+        contributes zeros and returns an empty gradient, so the other ranks never wait on it."""
         if self.tet_sp is None:
-            raise RuntimeError("this rank owns no spheres")
-        energy, grad = self.tet_sp.energy_grad(x_local, c1, c2, order, gradH)
+            energy = torch.zeros(3, dtype=torch.float32, device=self.device)
+            grad = torch.empty((0, 3), dtype=torch.float32, device=self.device)
+        else:
+            energy, grad = self.tet_sp.energy_grad(x_local, c1, c2, order, gradH)
+            energy = energy.clone()                 # the all-reduce must not write into the handle's energy ring
         if self.world_size > 1:
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.tet_sp.device))
+            ev.record(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
+                energy.record_stream(self._comm_stream)
                 self._work = allreduce_energy(energy, self.group, async_op=True)
         return energy, grad
 
@@ -95,5 +104,5 @@ class ShardedEnergy:
         """Block the current stream until the pending scalar all-reduce has landed."""
         if self._work is not None:
             self._work.wait()
-            torch.cuda.current_stream(self.tet_sp.device).wait_stream(self._comm_stream)
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
             self._work = None
