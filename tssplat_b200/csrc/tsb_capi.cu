@@ -218,6 +218,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
   kp.vh = plan.vh;
   kp.ring_bytes = tsb::energy_ring_bytes(ch.ring, cpc, plan.mode_global != 0);
   kp.cells_per_chunk = cpc;
+  kp.ring_slots = ch.ring;
   kp.stage_bytes = plan.mode_global ? 0 : plan.area_verts * 32;
   h->lc = tsb::LaunchConfig{nw, plan.grid, ch.smem, plan.mode_global, 0};
   h->amips = pc.enable_amips != 0;

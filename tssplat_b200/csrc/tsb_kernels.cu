@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     ws.bars = smem_u32(smem + off_bars(stage_bytes, NW, ring)) + warp * kMaxSlots * 8;
     ws.cpc = uint32_t(p.cells_per_chunk);
     ws.chunk_bytes = ws.cpc * CELL;
-    ws.nslot = uint32_t(ring) / ws.chunk_bytes;
+    ws.nslot = uint32_t(p.ring_slots);
     ws.cell = ws.ring;
     ws.cc = 0; ws.slot = 0; ws.phase = 0; ws.lane = lane;
     if (lane == 0) {

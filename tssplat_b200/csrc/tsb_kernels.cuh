@@ -40,6 +40,7 @@ struct KParams {
   int32_t vh;                   // STAGED: half-buffer capacity in vertices
   int32_t ring_bytes;           // per-warp ring size = slots * cells_per_chunk cells
   int32_t cells_per_chunk;      // cells per TMA bulk copy (= per ring slot)
+  int32_t ring_slots;
   int32_t stage_bytes;          // STAGED: bytes of the staging area at the start of shared memory
 #ifdef TSB_TRACE
   unsigned long long *trace;    // profiling build only: [grid][16] phase stamps

@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +79,40 @@ struct Mesh {
   std::vector<int32_t> local_of;  // [n] local id of a vertex inside its component
   int32_t lap_scale;
 };
+
+// Face adjacency of one component (faces never cross components): sort the 4 face keys of its tets and pair
+// equal neighbours.  Returns the number of boundary faces, or -1 for a face shared by more than two tets.
+int64_t build_adjacency(Mesh &M, const Comp &C) {
+  std::vector<FaceKey> fk(C.tets.size() * 4);
+  for (size_t i = 0; i < C.tets.size(); ++i) {
+    const int32_t t = C.tets[i];
+    const int32_t *v = M.tets + 4 * size_t(t);
+    for (int k = 0; k < 4; ++k) {
+      uint32_t f[3] = {uint32_t(v[kFace[k][0]]), uint32_t(v[kFace[k][1]]), uint32_t(v[kFace[k][2]])};
+      if (f[0] > f[1]) std::swap(f[0], f[1]);
+      if (f[1] > f[2]) std::swap(f[1], f[2]);
+      if (f[0] > f[1]) std::swap(f[0], f[1]);
+      fk[4 * i + k] = FaceKey{f[0], f[1], f[2], uint32_t(4 * t + k)};
+    }
+  }
+  std::sort(fk.begin(), fk.end());
+  int64_t boundary = 0;
+  const size_t nf = fk.size();
+  for (size_t i = 0; i < nf;) {
+    size_t j = i + 1;
+    while (j < nf && fk[j].same(fk[i])) ++j;
+    if (j - i > 2) return -1;
+    if (j - i == 2) {
+      const uint32_t o0 = fk[i].owner, o1 = fk[i + 1].owner;
+      M.nbr[o0] = int32_t(o1 >> 2);
+      M.nbr[o1] = int32_t(o0 >> 2);
+    } else {
+      ++boundary;
+    }
+    i = j;
+  }
+  return boundary;
+}
 
 // Rows of M = G^T L^T L G for one component, in fp64, off-diagonal entries rounded to fp32.
 //   F_t = sum_v x_v (x) a_{t,v}  (a = rest gradients of the hat functions: rows of Dm^-1, geometry/mesh_utils.py:38-69)
@@ -547,6 +583,9 @@ void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int 
 
 int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, const PlanConfig &cfg,
                HostPlan &P, std::string &err) {
+  const bool timing = std::getenv("TSSPLAT_B200_PLAN_TIMING") != nullptr;     // developer aid: phase times on stderr
+  auto t_last = std::chrono::steady_clock::now();
+#define TSB_T(name) do { if (timing) { auto t_now = std::chrono::steady_clock::now(); std::fprintf(stderr, "[plan] %-16s %.3f s\n", name, std::chrono::duration<double>(t_now - t_last).count()); t_last = t_now; } } while (0)
   if (!rest || !tets || n <= 0 || nele <= 0) { err = "null input or non-positive size"; return TSB_E_INVALID; }
   if (cfg.nw < 1 || cfg.nw > kMaxWarps || cfg.grid < 1) { err = "bad plan configuration"; return TSB_E_INVALID; }
   if (n >= 0xFFFFFF) { err = "more than 16.7 M vertices in one handle (row-block headers hold 24-bit row ids): shard the mesh"; return TSB_E_INVALID; }
@@ -571,40 +610,17 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     }
   }
 
+  TSB_T("validate");
   // ---- face adjacency (neighbour tet across each face) and vertex components -----------------------
   Mesh M{rest, tets, n, nele, std::vector<int32_t>(size_t(nele) * 4, -1), std::vector<int32_t>(size_t(n), -1), P.laplacian_scale};
   UnionFind uf(n);
   std::vector<uint8_t> used(n, 0);
-  {
-    std::vector<FaceKey> fk(size_t(nele) * 4);
-    for (int t = 0; t < nele; ++t) {
-      const int32_t *v = tets + 4 * size_t(t);
-      uf.unite(v[0], v[1]); uf.unite(v[0], v[2]); uf.unite(v[0], v[3]);
-      used[v[0]] = used[v[1]] = used[v[2]] = used[v[3]] = 1;
-      for (int k = 0; k < 4; ++k) {
-        uint32_t f[3] = {uint32_t(v[kFace[k][0]]), uint32_t(v[kFace[k][1]]), uint32_t(v[kFace[k][2]])};
-        if (f[0] > f[1]) std::swap(f[0], f[1]);
-        if (f[1] > f[2]) std::swap(f[1], f[2]);
-        if (f[0] > f[1]) std::swap(f[0], f[1]);
-        fk[4 * size_t(t) + k] = FaceKey{f[0], f[1], f[2], uint32_t(4 * t + k)};
-      }
-    }
-    std::sort(fk.begin(), fk.end());
-    const size_t nf = fk.size();
-    for (size_t i = 0; i < nf;) {
-      size_t j = i + 1;
-      while (j < nf && fk[j].same(fk[i])) ++j;
-      if (j - i > 2) { err = "non-manifold mesh: a face is shared by more than two tets"; return TSB_E_MESH; }
-      if (j - i == 2) {
-        const uint32_t o0 = fk[i].owner, o1 = fk[i + 1].owner;
-        M.nbr[o0] = int32_t(o1 >> 2);
-        M.nbr[o1] = int32_t(o0 >> 2);
-      } else {
-        ++P.n_boundary_faces;
-      }
-      i = j;
-    }
+  for (int t = 0; t < nele; ++t) {
+    const int32_t *v = tets + 4 * size_t(t);
+    uf.unite(v[0], v[1]); uf.unite(v[0], v[2]); uf.unite(v[0], v[3]);
+    used[v[0]] = used[v[1]] = used[v[2]] = used[v[3]] = 1;
   }
+  TSB_T("union-find");
   std::vector<Comp> comps;
   {
     std::vector<int32_t> label(n, -1);
@@ -626,13 +642,24 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   }
   const int NC = int(comps.size());
   P.n_components = NC;
-  // ---- operator rows, component-parallel ------------------------------------------------------------
+  TSB_T("components");
+  // ---- face adjacency, operator rows and bank-aware staging positions, component-parallel ---------------
+  bool global_mode = cfg.force_global || P.max_comp_verts > cfg.area_cap || P.max_comp_verts > kMaxStagedVerts;
+  const bool identity_first = global_mode || std::getenv("TSSPLAT_B200_NO_PLACEMENT") != nullptr;
   {
     int nth = cfg.threads > 0 ? cfg.threads : int(std::thread::hardware_concurrency());
     nth = std::max(1, std::min({nth, 32, NC}));
     std::atomic<int> next{0};
+    std::atomic<int64_t> boundary{0};
+    std::atomic<int> bad{0};
     auto work = [&]() {
-      for (int c = next.fetch_add(1); c < NC; c = next.fetch_add(1)) build_rows(M, comps[c]);
+      for (int c = next.fetch_add(1); c < NC; c = next.fetch_add(1)) {
+        const int64_t bf = build_adjacency(M, comps[c]);
+        if (bf < 0) { bad.store(1); continue; }
+        boundary.fetch_add(bf);
+        build_rows(M, comps[c]);
+        place_vertices(comps[c], identity_first);
+      }
     };
     if (nth == 1) {
       work();
@@ -641,14 +668,16 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       for (int i = 0; i < nth; ++i) th.emplace_back(work);
       for (auto &t : th) t.join();
     }
+    if (bad.load()) { err = "non-manifold mesh: a face is shared by more than two tets"; return TSB_E_MESH; }
+    P.n_boundary_faces = int32_t(boundary.load());
   }
 
+  TSB_T("adjacency+rows+placement");
   // ---- mode, bank-aware staging positions, staging capacities, grid ------------------------------------
-  bool global_mode = cfg.force_global || P.max_comp_verts > cfg.area_cap || P.max_comp_verts > kMaxStagedVerts;
-  auto place_all = [&](bool identity) {
+  auto place_all = [&](bool identity, bool redo) {
     int vh = 0, mx = 0;
     for (Comp &C : comps) {
-      place_vertices(C, identity);
+      if (redo) place_vertices(C, identity);
       mx = std::max(mx, C.npos);
       if (C.npos <= cfg.vh_cap) vh = std::max(vh, C.npos);
     }
@@ -657,7 +686,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     return mx;
   };
   if (!global_mode) {
-    const int mx = place_all(std::getenv("TSSPLAT_B200_NO_PLACEMENT") != nullptr);
+    const int mx = place_all(identity_first, false);
     if (mx > cfg.area_cap || mx > kMaxStagedVerts) global_mode = true;     // colouring padded a borderline component over the cap
   }
   int G = cfg.grid;
@@ -666,8 +695,9 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   P.grid = G;
   P.mode_global = global_mode ? 1 : 0;
   const bool GLOBAL = global_mode;
-  if (GLOBAL) { place_all(true); P.vh = 0; P.area_verts = 0; }
+  if (GLOBAL) { place_all(true, !identity_first); P.vh = 0; P.area_verts = 0; }
 
+  TSB_T("placement");
   // ---- cost stream and its G cuts --------------------------------------------------------------------
   const double CR = 2.0, CT = double(cfg.tet_cost);
   std::vector<double> crow(NC), ctot(NC), cbase(size_t(NC) + 1, 0.0);
@@ -778,6 +808,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     h.p4off = GLOBAL ? 0 : p4off[g.comp];
   }
 
+  TSB_T("segments+tables");
   // ---- per-warp streams ----------------------------------------------------------------------------------
   P.wseg.assign(size_t(NS) * NW * 2, 0);
   P.wdesc.assign(size_t(G) * NW * 2, 0);
@@ -912,6 +943,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
       }
     if (P.Bt.size() != cells * per_cell) { err = "internal: AMIPS rest-inverse blocks out of step with the tet cells"; return TSB_E_INVALID; }
   }
+  TSB_T("emission");
   size_t total = 0;
   for (const auto &st : wstream) total += st.size();
   if (total / 16 > 0xFFFFFFFFull) { err = "plan stream exceeds 64 GiB"; return TSB_E_NOMEM; }
@@ -925,6 +957,7 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
     if (st.size() > 0xFFFFFFFFull) { err = "warp stream exceeds 4 GiB"; return TSB_E_NOMEM; }
     off += st.size();
   }
+  TSB_T("concat");
   return TSB_OK;
 }
 
