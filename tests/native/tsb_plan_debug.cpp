@@ -27,6 +27,7 @@ int tsbdbg_build(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t 
   if (area_cap > 0) pc.area_cap = area_cap;
   if (tet_cost > 0) pc.tet_cost = tet_cost;
   if (const char *e = std::getenv("TSB_RB_CAP_DIV")) pc.rb_cap_div = std::atoi(e);
+  if (const char *e = std::getenv("TSB_SEG_OVERHEAD_X100")) pc.seg_overhead = float(std::atoi(e)) / 100.f;
   tsbdbg_plan *d = new tsbdbg_plan();
   const int rc = tsb::build_plan(rest_xyz, tets, n, nele, pc, d->plan, g_err);
   if (rc != TSB_OK) { delete d; return rc; }

@@ -458,3 +458,17 @@ def test_amips_term_default_off(ext):
     assert abs(float(e[3])) < 1e-3 and float(g.abs().max()) < 1e-3
     with pytest.raises(RuntimeError, match="enable_amips"):
         plain.energy_grad(rest, 1.0, 1.0, 2, c3=0.5)
+
+
+def test_handles_with_different_staging_sizes_coexist(ext):
+    """The dynamic shared-memory opt-in is per kernel, not per handle: a small-staging handle created after a
+    large one must not shrink it (bench.py keeps 8 packs alive)."""
+    big = make_pack(2, 4096, seed=31)
+    small = make_pack(3, 512, seed=32)
+    a = ext.TetSpheres(big.verts.reshape(-1), big.tets.reshape(-1))
+    b = ext.TetSpheres(small.verts.reshape(-1), small.tets.reshape(-1))
+    assert a.info["smem_bytes"] > b.info["smem_bytes"]
+    xa = torch.from_numpy(perturb(big, sigma_rel=0.3, seed=1)).cuda()
+    e, g = a.energy_grad(xa, 1e-4, 2e-4, 2)
+    eo, _, go = COracle(big.verts, big.tets).energy_grad(xa.cpu().numpy(), 1e-4, 2e-4, 2)
+    assert float(e[0]) == pytest.approx(eo, rel=REL) and np.linalg.norm(g.cpu().numpy() - go) <= REL * np.linalg.norm(go)

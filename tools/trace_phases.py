@@ -62,6 +62,21 @@ def run(sizes):
                   " / ".join(f"{v:.0f}" for v in np.median(ext, 0)) +
                   f"; warp0 first RB len4 median {np.median(info & 0xFFFF):.0f}, RBs {np.median((info >> 16) & 0xFF):.0f}, tet cells {np.median((info >> 24) & 0xFF):.0f}")
             post = (tr[:, 9] - tr[:, 3]) / 1.965        # after griddepcontrol.wait -> partial stored
+            try:                                         # correlate with the plan (host-side inspection library)
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from _helpers import build_host_plan
+                pl = build_host_plan(pack.verts, pack.tets, nw=sp.info["warps_per_cta"], grid=G)
+                NWp = pl["nw"]
+                cells = pl["wdesc"].reshape(G, NWp, 2)[:, :, 1] // 768
+                nseg = np.diff(pl["cta_seg"].reshape(G, 2), axis=1).ravel()
+                ws_ = pl["wseg"].reshape(-1, NWp, 2)
+                rbs = np.array([ws_[a:b, :, 0].sum() for a, b in pl["cta_seg"].reshape(G, 2)])
+                for k in sorted(set(nseg.tolist())):
+                    m = nseg == k
+                    print(f"    CTAs with {k} segment(s): {m.sum():3d}  post-wait mean {post[m].mean():.0f} ns  total cells {cells[m].sum(1).mean():.0f}  "
+                          f"max warp cells {cells[m].max(1).mean():.1f}  row blocks {rbs[m].mean():.1f}  stage {d[m, 2].mean():.0f}  rows(w0,seg0) {d[m, 3].mean():.0f}  rest {d[m, 5].mean():.0f}")
+            except Exception as ex:
+                print("    (plan correlation unavailable:", ex, ")")
             pct = np.percentile(post, [0, 25, 50, 75, 90, 100])
             worst = int(np.argmax(post))
             print("    post-wait work per CTA (ns): min/25/50/75/90/max = " + "/".join(f"{v:.0f}" for v in pct) +

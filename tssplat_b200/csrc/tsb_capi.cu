@@ -15,10 +15,11 @@ struct tsb_handle_s {
   int device = 0;
   tsb::KParams kp{};
   tsb::LaunchConfig lc{};
-  // tsb_energy_grad_host: double-buffered upload staging on an internal copy stream
-  float *stage_x[2] = {nullptr, nullptr}, *stage_grad = nullptr, *stage_energy = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  // tsb_energy_grad_host: a three-stage pipeline on internal streams (upload | kernel | download), every
+  // buffer double-buffered, so call i+1's upload and kernel overlap call i's download
+  float *stage_x[2] = {nullptr, nullptr}, *stage_grad[2] = {nullptr, nullptr}, *stage_energy[2] = {nullptr, nullptr};
+  cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   unsigned host_calls = 0;
   bool amips = false;
   tsb_info_t info{};
@@ -160,6 +161,7 @@ int tsb_create(const float *rest_xyz, const int32_t *tets, int32_t n, int32_t ne
 
   pc.ring_cells = env_int("TSSPLAT_B200_NO_SPLIT", 0) ? 0 : ring * cpc;
   pc.rb_cap_div = std::max(1, env_int("TSSPLAT_B200_RB_CAP_DIV", pc.rb_cap_div));
+  if (env_int("TSSPLAT_B200_SEG_OVERHEAD_X100", -1) >= 0) pc.seg_overhead = float(env_int("TSSPLAT_B200_SEG_OVERHEAD_X100", 25)) / 100.f;
   tsb::HostPlan plan;
   std::string err;
   int rc = tsb::build_plan(rest_xyz, tets, n, nele, pc, plan, err);
@@ -241,10 +243,13 @@ void tsb_destroy(tsb_handle_t h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   for (int k = 0; k < 2; ++k) {
-    if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
-    if (h->ev_free[k]) cudaEventDestroy(h->ev_free[k]);
+    if (h->ev_up[k]) cudaEventDestroy(h->ev_up[k]);
+    if (h->ev_run[k]) cudaEventDestroy(h->ev_run[k]);
+    if (h->ev_down[k]) cudaEventDestroy(h->ev_down[k]);
   }
-  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->s_up) cudaStreamDestroy(h->s_up);
+  if (h->s_run) cudaStreamDestroy(h->s_run);
+  if (h->s_down) cudaStreamDestroy(h->s_down);
   for (void *p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -297,41 +302,58 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
   if (!guard.ok) return fail(h, TSB_E_CUDA, "cannot select the handle's CUDA device");
   const size_t nb = size_t(h->info.n) * 3 * sizeof(float);
   if (!h->stage_x[0]) {
-    int rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x[0]);
-    if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x[1]);
-    if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_grad);
-    if (rc == TSB_OK) rc = alloc_zero(h, 4, &h->stage_energy);
-    if (rc != TSB_OK) return rc;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-      e = cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_free[k], cudaEventDisableTiming);
+    int rc = TSB_OK;
+    for (int k = 0; k < 2 && rc == TSB_OK; ++k) {
+      rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_x[k]);
+      if (rc == TSB_OK) rc = alloc_zero(h, size_t(h->info.n) * 3, &h->stage_grad[k]);
+      if (rc == TSB_OK) rc = alloc_zero(h, 4, &h->stage_energy[k]);
     }
-    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("copy stream setup: ") + cudaGetErrorString(e));
+    if (rc != TSB_OK) return rc;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_run[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_down[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("pipeline stream setup: ") + cudaGetErrorString(e));
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   const int k = int(h->host_calls & 1u);
   cudaError_t e;
-  if (cap == cudaStreamCaptureStatusNone) {
-    // upload on the copy stream as soon as the kernel that last read this staging buffer is done:
-    // overlaps the previous call's kernel + download
-    ++h->host_calls;
-    e = cudaStreamWaitEvent(h->copy_stream, h->ev_free[k], 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, h->copy_stream);
-    if (e == cudaSuccess) e = cudaEventRecord(h->ev_h2d[k], h->copy_stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_h2d[k], 0);
-  } else {
-    e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, st);   // inside a stream capture: keep it linear
+  if (cap != cudaStreamCaptureStatusNone) {      // inside a stream capture: keep it linear on the caller's stream
+    e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+    const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy[k],
+                                   grad_out_host ? h->stage_grad[k] : nullptr, stream);
+    if (rc != TSB_OK) return rc;
+    e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad[k], nb, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
+    return TSB_OK;
   }
+  ++h->host_calls;
+  // upload: as soon as the kernel that last read this staging buffer (two calls ago) is done
+  e = cudaStreamWaitEvent(h->s_up, h->ev_run[k], 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, h->s_up);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev_up[k], h->s_up);
+  // kernel: after its upload, and after the download that last read these output buffers (two calls ago)
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_up[k], 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_down[k], 0);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-  const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy,
-                                 grad_out_host ? h->stage_grad : nullptr, stream);
+  const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy[k],
+                                 grad_out_host ? h->stage_grad[k] : nullptr, h->s_run);
   if (rc != TSB_OK) return rc;
-  if (cap == cudaStreamCaptureStatusNone) e = cudaEventRecord(h->ev_free[k], st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy, 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad, nb, cudaMemcpyDeviceToHost, st);
+  e = cudaEventRecord(h->ev_run[k], h->s_run);
+  // download, then make the caller's stream wait for it (so synchronising `stream` completes the call)
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_down, h->ev_run[k], 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_down);
+  if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad[k], nb, cudaMemcpyDeviceToHost, h->s_down);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev_down[k], h->s_down);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_down[k], 0);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
   return TSB_OK;
 }

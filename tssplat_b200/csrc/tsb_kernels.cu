@@ -250,10 +250,51 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     }
   };
 
+  // The first TWO components are staged before the first barrier (they use different half-buffers), so no
+  // CTA-wide barrier separates segments 0 and 1: a warp flows from its work in the first into the second
+  // (at <= 64 spheres per GPU no CTA has more than two segments).
+  bool eager2 = false;
   if (!GLOBAL) {
     if (cs.x < cs.y) {
-      if (hcur.whole) stage_direct(hcur, 0);
-      else { load_x(hcur); store_staged(hcur, 0); }
+      SegHdr h1{};
+      if (cs.x + 1 < cs.y && !hcur.whole) {
+        h1 = p.segs[cs.x + 1];
+        eager2 = !h1.whole;
+      }
+      if (hcur.whole) {
+        stage_direct(hcur, 0);
+      } else if (!eager2) {
+        load_x(hcur); store_staged(hcur, 0);
+      } else {
+        // both components' loads in flight together (second register set), then both stores
+        float qx[SV][3];
+        float4 qX[SV];
+#pragma unroll
+        for (int k = 0; k < SV; ++k) {
+          const int v = tid + k * NT;
+          if (v < h1.nv) { qX[k] = __ldg(&p.X4[h1.x4off + v]); qX[k].w = __uint_as_float(uint32_t(__ldg(&p.pos16[h1.x4off + v]))); }
+        }
+        load_x(hcur);
+#pragma unroll
+        for (int k = 0; k < SV; ++k) {
+          const int v = tid + k * NT;
+          if (v < h1.nv) {
+            const size_t gi = size_t(h1.vbase >= 0 ? h1.vbase + v : __ldg(&p.vlist[h1.x4off + v]));
+            qx[k][0] = __ldcg(p.x + 3 * gi); qx[k][1] = __ldcg(p.x + 3 * gi + 1); qx[k][2] = __ldcg(p.x + 3 * gi + 2);
+          }
+        }
+        store_staged(hcur, 0);
+        float4 *ub = stage + ubase_of(h1, 1), *xb = stage + xbase_of(h1, 1);
+#pragma unroll
+        for (int k = 0; k < SV; ++k) {
+          const int v = tid + k * NT;
+          if (v < h1.nv) {
+            const uint32_t pos = __float_as_uint(qX[k].w);
+            ub[pos] = make_float4(qx[k][0] - qX[k].x, qx[k][1] - qX[k].y, qx[k][2] - qX[k].z, 0.f);
+            xb[pos] = make_float4(qx[k][0], qx[k][1], qx[k][2], 0.f);
+          }
+        }
+      }
     }
     __syncthreads();
     TSB_STAMP(4);
@@ -272,7 +313,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     if (s + 1 < cs.y) {
       hn = seg_at(s + 1);
       if (!GLOBAL) {
-        pre = !hcur.whole && !hn.whole;
+        pre = !hcur.whole && !hn.whole && !(li == 0 && eager2);
         if (pre) {
 #pragma unroll
           for (int k = 0; k < SV; ++k) {
@@ -354,11 +395,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     if (s == cs.x) TSB_STAMP(5);
     if (grad) {   // all warps' rows of this segment are stored -> ONE release of the component's counter, sent by
                   // the last warp (which owns no tets, so it never waits on its own signal)
+      const int bar_id = 1 + (li & 1);      // segments 0 and 1 may be in flight together: two barrier ids
       if (warp == NW - 1) {
-        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
         if (lane == 0) { __threadfence(); atomicAdd(p.done + hcur.comp, 1u); }
       } else {
-        asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");
+        asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
       }
     }
 
@@ -474,11 +516,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
 
     // ---- hand the staging buffers over ------------------------------------------------------------------
     if (!GLOBAL) {
-      if (pre) store_staged(hn, li + 1);
-      __syncthreads();
-      if (s + 1 < cs.y && !pre) {
-        stage_direct(hn, li + 1);
+      if (li == 0 && eager2) {
+        // segment 1 is already staged: no barrier
+      } else {
+        if (pre) {
+          if (li == 1 && eager2) __syncthreads();     // half 0 is reused: every warp must have left segment 0
+          store_staged(hn, li + 1);
+        }
         __syncthreads();
+        if (s + 1 < cs.y && !pre) {
+          stage_direct(hn, li + 1);
+          __syncthreads();
+        }
       }
     } else if (grad) {
       __syncthreads();     // keeps the named barrier's generations apart
@@ -649,9 +698,16 @@ cudaError_t launch_variant(const KParams &p, const LaunchConfig &lc, cudaStream_
 
 template <int NW, int MINB, bool GLOBAL>
 cudaError_t occupancy_variant(int smem_bytes, bool amips, int *ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e == cudaSuccess && amips) e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) { *ctas_per_sm = 0; cudaGetLastError(); return cudaSuccess; }   // does not fit
+  // opt in to the device maximum once (the attribute is per function, not per handle: handles with different
+  // staging sizes share the kernel)
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  if (smem_bytes > optin) { *ctas_per_sm = 0; return cudaSuccess; }   // does not fit
+  e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (e == cudaSuccess && amips) e = cudaFuncSetAttribute(energy_grad_kernel<NW, MINB, GLOBAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (e != cudaSuccess) { *ctas_per_sm = 0; cudaGetLastError(); return cudaSuccess; }
   int a = 0, b = 1 << 30;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, energy_grad_kernel<NW, MINB, GLOBAL, false>, NW * 32, size_t(smem_bytes));
   if (e == cudaSuccess && amips) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, energy_grad_kernel<NW, MINB, GLOBAL, true>, NW * 32, size_t(smem_bytes));

@@ -715,16 +715,44 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   cuts[0] = {0, 0.0};
   cuts[G] = {NC - 1, 1.0};
   {
-    int c = 0;
-    for (int b = 1; b < G; ++b) {
-      const double p = W * double(b) / double(G);
-      while (c + 1 < NC && cbase[c + 1] <= p) ++c;
-      double f = ctot[c] > 0 ? (p - cbase[c]) / ctot[c] : 0.0;
-      const double eps = std::min(0.05, 0.15 * (W / G) / std::max(ctot[c], 1e-30));
-      if (f < eps) f = 0.0;
-      if (f > 1.0 - eps) f = 1.0;
-      cuts[b] = {c, f};
+    // Every segment a CTA touches costs a fixed overhead F on top of its share of the stream (staging its
+    // component, a second set of partially filled row blocks): CTAs are filled greedily up to a capacity T
+    // that includes F per segment, and T is found by bisection so that exactly G CTAs consume the stream.
+    const double F = double(cfg.seg_overhead) * W / G;
+    auto fill = [&](double T, std::vector<Cut> *out) -> int {
+      int b = 0, c = 0;
+      double f = 0.0;                       // position inside component c
+      if (out) (*out)[0] = {0, 0.0};
+      while (c < NC) {
+        double cap = T - F;                 // first segment of this CTA
+        while (c < NC && cap > 0) {
+          const double rem = (1.0 - f) * ctot[c];
+          if (rem <= cap * 1.02) {          // take the rest of the component (2% slack avoids slivers)
+            cap -= rem; ++c; f = 0.0;
+            if (c < NC) { cap -= F; if (cap < 0.10 * T) break; }      // not worth opening another segment
+          } else {
+            const double eps = std::min(0.05, 0.15 * T / std::max(ctot[c], 1e-30));
+            double nf = f + cap / ctot[c];
+            if (nf - f < eps) break;        // sliver: leave it to the next CTA
+            if (nf > 1.0 - eps) nf = 1.0;
+            f = nf; cap = 0;
+            if (f >= 1.0) { ++c; f = 0.0; }
+          }
+        }
+        ++b;
+        if (out && b <= G) (*out)[b] = (c >= NC) ? Cut{NC - 1, 1.0} : Cut{c, f};
+        if (b > 4 * G + 8) break;
+      }
+      return b;
+    };
+    double lo = W / G, hi = W + F * (NC + 1) + 1.0;      // hi: one CTA could take everything
+    for (int it = 0; it < 64; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      if (fill(mid, nullptr) <= G) hi = mid; else lo = mid;
     }
+    const int used = fill(hi, &cuts);
+    for (int b = std::min(used, G); b <= G; ++b) cuts[b] = {NC - 1, 1.0};   // unused CTAs (tiny meshes) get nothing
+    cuts[G] = {NC - 1, 1.0};
     for (int b = 1; b <= G; ++b) {   // monotone
       const Cut &a = cuts[b - 1];
       Cut &d = cuts[b];

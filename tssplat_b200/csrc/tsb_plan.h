@@ -78,6 +78,7 @@ struct PlanConfig {
   float tetcell_cost = 1.3f;    // cost of one tet cell relative to one quad cell (warp-level deal)
   int32_t max_lanes_per_row = 4;   // rows may be split over up to this many adjacent lanes (latency regime only)
   int32_t ring_cells = 12;         // cells one warp's TMA ring holds (decides the latency / streaming regime)
+  float seg_overhead = 0.60f;      // fixed cost of every (CTA, component) segment, as a fraction of the mean CTA cost
   int32_t rb_cap_div = 2;          // latency regime: a row block is at most ring_cells / rb_cap_div cells
   int32_t threads = 0;          // host threads for the build (0 = hardware concurrency, capped)
   int32_t enable_amips = 0;     // also emit the per-tet rest inverses (AMIPS term; 48 B per tet)
