@@ -33,6 +33,11 @@ import sys
 import threading
 import time
 
+try:      # before anything can start an OpenMP region: OMP_PROC_BIND narrows the main thread's mask to its own place
+    _AFFINITY0 = frozenset(os.sched_getaffinity(0))
+except Exception:
+    _AFFINITY0 = None
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -126,10 +131,9 @@ class ClockSampler(threading.Thread):
 
 # ---- CPU arms ------------------------------------------------------------------------------------------
 def _host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+    """Hardware threads this process was given at start-up (NOT the current mask: once libgomp has bound the
+    main thread to its place, sched_getaffinity reports that one core only)."""
+    return len(_AFFINITY0) if _AFFINITY0 else (os.cpu_count() or 1)
 
 
 def _c_oracle(pack, variant=""):

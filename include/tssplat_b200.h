@@ -120,9 +120,10 @@ int tsb_energy_grad_ex(tsb_handle_t h, const float *x_dev, const tsb_terms_t *te
 /* Same computation for callers whose vertex positions live in HOST memory (e.g. a CPU-side
  * optimiser): copies x_host -> device, runs the fused launch, copies energy[3] and grad back,
  * asynchronously; the outputs are valid once `stream` has been synchronised and the host buffers
- * must stay valid until then (pinned memory makes the copies truly asynchronous).  The three stages
- * (upload, kernel, download) run on internal streams with double-buffered staging, so successive calls
- * pipeline: call i+1's upload and kernel overlap call i's download.  Consequences: x_host must be fully
+ * must stay valid until then (pinned memory makes the copies truly asynchronous).  Calls
+ * alternate between two internal streams (upload -> kernel -> download, each with its own staging buffers;
+ * only the kernels are ordered across the two), so successive calls pipeline: call i+1's upload overlaps
+ * call i's kernel and download.  Consequences: x_host must be fully
  * written by the CPU when the call is made (the upload is NOT ordered after earlier work queued on
  * `stream`), and the handle must not be used through tsb_energy_grad on another stream until `stream` has
  * been synchronised.  grad_out_host may be NULL.

@@ -15,11 +15,14 @@ struct tsb_handle_s {
   int device = 0;
   tsb::KParams kp{};
   tsb::LaunchConfig lc{};
-  // tsb_energy_grad_host: a three-stage pipeline on internal streams (upload | kernel | download), every
-  // buffer double-buffered, so call i+1's upload and kernel overlap call i's download
+  // tsb_energy_grad_host: calls alternate between two internal streams, each running upload -> kernel ->
+  // download on its own staging buffers; only the kernels are ordered across the two (ev_run), so call
+  // i+1's upload overlaps call i's kernel and download.  (Measured on the pool's B200 hosts: 31.6 us per call
+  // for 0.64 MB each way; a third stream for the downloads, or one stream per stage, costs 2.5x the CPU time
+  // per call in the driver and ends up slower: 46-49 us.)
   float *stage_x[2] = {nullptr, nullptr}, *stage_grad[2] = {nullptr, nullptr}, *stage_energy[2] = {nullptr, nullptr};
-  cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
-  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
+  cudaStream_t s_pipe[2] = {nullptr, nullptr};
+  cudaEvent_t ev_run[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   unsigned host_calls = 0;
   bool amips = false;
   tsb_info_t info{};
@@ -34,11 +37,12 @@ thread_local std::string g_create_err;
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
-  explicit DeviceGuard(int dev) {
+  explicit DeviceGuard(int d) : dev(d) {
     if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
     if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
   }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  int dev;
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };
 
 // device that owns a device pointer (falls back to the current device)
@@ -243,13 +247,10 @@ void tsb_destroy(tsb_handle_t h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   for (int k = 0; k < 2; ++k) {
-    if (h->ev_up[k]) cudaEventDestroy(h->ev_up[k]);
     if (h->ev_run[k]) cudaEventDestroy(h->ev_run[k]);
-    if (h->ev_down[k]) cudaEventDestroy(h->ev_down[k]);
+    if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+    if (h->s_pipe[k]) cudaStreamDestroy(h->s_pipe[k]);
   }
-  if (h->s_up) cudaStreamDestroy(h->s_up);
-  if (h->s_run) cudaStreamDestroy(h->s_run);
-  if (h->s_down) cudaStreamDestroy(h->s_down);
   for (void *p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -309,13 +310,11 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
       if (rc == TSB_OK) rc = alloc_zero(h, 4, &h->stage_energy[k]);
     }
     if (rc != TSB_OK) return rc;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking);
+    cudaError_t e = cudaSuccess;
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-      e = cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming);
+      e = cudaStreamCreateWithFlags(&h->s_pipe[k], cudaStreamNonBlocking);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_run[k], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_down[k], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("pipeline stream setup: ") + cudaGetErrorString(e));
   }
@@ -336,24 +335,21 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
     return TSB_OK;
   }
   ++h->host_calls;
-  // upload: as soon as the kernel that last read this staging buffer (two calls ago) is done
-  e = cudaStreamWaitEvent(h->s_up, h->ev_run[k], 0);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, h->s_up);
-  if (e == cudaSuccess) e = cudaEventRecord(h->ev_up[k], h->s_up);
-  // kernel: after its upload, and after the download that last read these output buffers (two calls ago)
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_up[k], 0);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_down[k], 0);
+  // stream k: upload (ordered after call i-2's download of the same buffers by stream order) ...
+  cudaStream_t sk = h->s_pipe[k];
+  e = cudaMemcpyAsync(h->stage_x[k], x_host, nb, cudaMemcpyHostToDevice, sk);
+  // ... kernel, after the previous call's kernel on the other stream (the handle's counters are shared) ...
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, h->ev_run[k ^ 1], 0);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
   const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy[k],
-                                 grad_out_host ? h->stage_grad[k] : nullptr, h->s_run);
+                                 grad_out_host ? h->stage_grad[k] : nullptr, sk);
   if (rc != TSB_OK) return rc;
-  e = cudaEventRecord(h->ev_run[k], h->s_run);
-  // download, then make the caller's stream wait for it (so synchronising `stream` completes the call)
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_down, h->ev_run[k], 0);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_down);
-  if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad[k], nb, cudaMemcpyDeviceToHost, h->s_down);
-  if (e == cudaSuccess) e = cudaEventRecord(h->ev_down[k], h->s_down);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_down[k], 0);
+  e = cudaEventRecord(h->ev_run[k], sk);
+  // ... download; the caller's stream waits for it, so synchronising `stream` completes the call
+  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, sk);
+  if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad[k], nb, cudaMemcpyDeviceToHost, sk);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev_done[k], sk);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_done[k], 0);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e));
   return TSB_OK;
 }

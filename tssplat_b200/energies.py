@@ -24,14 +24,10 @@ class SmoothnessBarrierFunc(torch.autograd.Function):
     ``None`` grad_output."""
 
     @staticmethod
-    def forward(x_cur, tet_sp, c1, c2, order):
-        return tet_spheres_ext.forward(x_cur, tet_sp, c1, c2, order)
-
-    @staticmethod
-    def setup_context(ctx, inputs, output):
-        x_cur, tet_sp, c1, c2, order = inputs
+    def forward(ctx, x_cur, tet_sp, c1, c2, order):      # ctx-style like the reference's (no per-call signature binding)
         ctx.save_for_backward(x_cur)
         ctx.constants = (tet_sp, c1, c2, order)
+        return tet_spheres_ext.forward(x_cur, tet_sp, c1, c2, order)
 
     @staticmethod
     def backward(ctx, grad_output):

@@ -62,12 +62,13 @@ class AdamUniform(torch.optim.Optimizer):
                     if self.grad_limit_ptr < len(self.grad_limit_iters):            # :79-81
                         if self.cc >= self.grad_limit_iters[self.grad_limit_ptr]:
                             self.grad_limit_ptr += 1
-                grad = p.grad.data.contiguous()
-                with torch.cuda.device(p.device):
-                    rc = _capi.lib.tsb_adam_uniform_step(
-                        p.data.data_ptr(), grad.data_ptr(), state["g1"].data_ptr(), state["g2"].data_ptr(), p.numel(),
-                        float(lr), float(b1), float(b2), int(state["step"]), limit, state["_work"].data_ptr(),
-                        int(torch.cuda.current_stream(p.device).cuda_stream))
-                _capi.check(rc, None, "AdamUniform.step")
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                # the C ABI selects the device that owns p (no torch.cuda.device context needed)
+                rc = _capi.lib.tsb_adam_uniform_step(
+                    p.data_ptr(), grad.data_ptr(), state["g1"].data_ptr(), state["g2"].data_ptr(), p.numel(),
+                    float(lr), float(b1), float(b2), int(state["step"]), limit, state["_work"].data_ptr(),
+                    _ext._stream_ptr(p.device))
+                if rc:
+                    _capi.check(rc, None, "AdamUniform.step")
                 _ext.note_parameters_changed()         # p.data changed without bumping p._version
                 self.cc += 1                                   # :89

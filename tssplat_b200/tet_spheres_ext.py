@@ -40,7 +40,14 @@ _limit_work = {}       # (device, stream) -> float32[4] scratch of grad_limit (c
 fuse_backward_into_forward = True
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (the raw query when torch exposes it: the public
+    ``torch.cuda.current_stream`` costs several microseconds per call)."""
+    if _raw_stream is not None:
+        return int(_raw_stream(device.index if isinstance(device, torch.device) else int(device)))
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -98,6 +105,9 @@ class TetSpheres:
         # energies of the last 32 launches (a ring, so a loss tensor stays valid while it is being logged)
         self._energy_ring = torch.zeros((32, 4), dtype=torch.float32, device=self.device)
         self._ring_i = 0
+        self._ring_ptr = self._energy_ring.data_ptr()
+        self._ring3 = [self._energy_ring[i, :3] for i in range(32)]       # views made once, not per launch
+        self._ring4 = [self._energy_ring[i] for i in range(32)]
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -125,7 +135,8 @@ class TetSpheres:
         xc = self._check_x(x)
         i = self._ring_i
         self._ring_i = (i + 1) & 31
-        energy = self._energy_ring[i] if c3 else self._energy_ring[i, :3]
+        energy = self._ring4[i] if c3 else self._ring3[i]
+        e_ptr = self._ring_ptr + 16 * i
         grad = torch.empty((self.n, 3), dtype=torch.float32, device=self.device) if want_grad else None
         gh_val, gh_ptr, keep = 1.0, None, None
         if isinstance(gradH, torch.Tensor):
@@ -138,11 +149,11 @@ class TetSpheres:
             gh_val = float(gradH)
         if c3:
             terms = _capi.tsb_terms_t(c1=float(c1), c2=float(c2), order=int(order), c3=float(c3))
-            rc = _capi.lib.tsb_energy_grad_ex(self._h, xc.data_ptr(), C.byref(terms), gh_val, gh_ptr, energy.data_ptr(),
+            rc = _capi.lib.tsb_energy_grad_ex(self._h, xc.data_ptr(), C.byref(terms), gh_val, gh_ptr, e_ptr,
                                               grad.data_ptr() if want_grad else None, _stream_ptr(self.device))
         else:
             rc = _capi.lib.tsb_energy_grad(self._h, xc.data_ptr(), float(c1), float(c2), int(order), gh_val,
-                                           gh_ptr, energy.data_ptr(), grad.data_ptr() if want_grad else None,
+                                           gh_ptr, e_ptr, grad.data_ptr() if want_grad else None,
                                            _stream_ptr(self.device))
         if rc:
             _capi.check(rc, self._h, "tet_spheres_ext")
@@ -229,7 +240,7 @@ def grad_limit(grad: torch.Tensor, s_threshold: float, s: float) -> None:
     (the intent of ``tet_spheres_cuda.cu:265-303``)."""
     if not grad.is_cuda or grad.dtype != torch.float32 or not grad.is_contiguous():
         raise RuntimeError("grad_limit needs a contiguous float32 CUDA tensor")
-    key = (grad.device.index, int(torch.cuda.current_stream(grad.device).cuda_stream))
+    key = (grad.device.index, _stream_ptr(grad.device))
     work = _limit_work.get(key)
     if work is None:
         work = _limit_work[key] = torch.zeros(4, dtype=torch.float32, device=grad.device)
