@@ -200,6 +200,23 @@ def test_host_buffer_entry_point(ext):
     assert float(e_host[0]) == pytest.approx(eo, rel=REL)
     with pytest.raises(RuntimeError):
         ext.energy_grad_host(sp, x_host[:-1], 1e-4, 2e-4, 4, 0.5, e_host, g_host)
+    # pageable host buffers (no device alias for the energy, staged copies) give the same answer
+    x_pg, g_pg, e_pg = torch.from_numpy(x_np.copy()), torch.zeros((pack.n, 3)), torch.zeros(3)
+    ext.energy_grad_host(sp, x_pg, 1e-4, 2e-4, 4, 0.5, e_pg, g_pg)
+    torch.cuda.synchronize()
+    assert float(e_pg[0]) == pytest.approx(float(e_host[0]), rel=1e-6)
+    assert (g_pg - g_host).norm() <= 1e-6 * g_host.norm()      # inverted tets: atomics, equal to rounding
+    # a pipelined burst of calls with different inputs: every call's outputs belong to its own input
+    xs = [torch.from_numpy(perturb(pack, sigma_rel=0.01 * (i + 1), seed=10 + i)).pin_memory() for i in range(6)]
+    gs = [torch.empty((pack.n, 3)).pin_memory() for _ in xs]
+    es = [torch.empty(3).pin_memory() for _ in xs]
+    for xi, gi, ei in zip(xs, gs, es):
+        ext.energy_grad_host(sp, xi, 1e-4, 2e-4, 2, 1.0, ei, gi)
+    torch.cuda.synchronize()
+    for xi, gi, ei in zip(xs, gs, es):
+        e1, g1 = sp.energy_grad(xi.cuda(), 1e-4, 2e-4, 2)
+        assert float(ei[0]) == pytest.approx(float(e1[0]), rel=1e-6)
+        assert (gi - g1.cpu()).norm() <= 1e-6 * g1.norm().cpu()
 
 
 def test_construct_from_veg_file(ext, tmp_path):

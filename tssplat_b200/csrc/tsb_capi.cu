@@ -341,12 +341,24 @@ int tsb_energy_grad_host(tsb_handle_t h, const float *x_host, float c1, float c2
   // ... kernel, after the previous call's kernel on the other stream (the handle's counters are shared) ...
   if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, h->ev_run[k ^ 1], 0);
   if (e != cudaSuccess) return fail(h, TSB_E_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
-  const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, h->stage_energy[k],
+  // pinned + mapped host memory has a device alias (UVA): the kernel stores the 3 floats there itself, one copy
+  // less per call (looked up every call: the address may have been freed and reused as pageable memory)
+  float *e_alias = nullptr;
+  {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, energy_out_host) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer)
+      e_alias = static_cast<float *>(a.devicePointer);
+    else
+      cudaGetLastError();
+  }
+  float *e_dst = e_alias ? e_alias : h->stage_energy[k];
+  const int rc = tsb_energy_grad(h, h->stage_x[k], c1, c2, order, gradH, nullptr, e_dst,
                                  grad_out_host ? h->stage_grad[k] : nullptr, sk);
   if (rc != TSB_OK) return rc;
   e = cudaEventRecord(h->ev_run[k], sk);
   // ... download; the caller's stream waits for it, so synchronising `stream` completes the call
-  if (e == cudaSuccess) e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, sk);
+  if (e == cudaSuccess && !e_alias)
+    e = cudaMemcpyAsync(energy_out_host, h->stage_energy[k], 3 * sizeof(float), cudaMemcpyDeviceToHost, sk);
   if (e == cudaSuccess && grad_out_host) e = cudaMemcpyAsync(grad_out_host, h->stage_grad[k], nb, cudaMemcpyDeviceToHost, sk);
   if (e == cudaSuccess) e = cudaEventRecord(h->ev_done[k], sk);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_done[k], 0);
