@@ -333,11 +333,15 @@ def main():
         for w in range(args.warmup):
             launch(w % n_rotate, stream.cuda_stream)
         stream.synchronize()
-    graph = graph_of(lambda k: launch(k, stream.cuda_stream), n_rotate)
+    # one replay = `rounds` passes over the rotating packs (~1 ms of device work), so that neither the replay call
+    # nor, under torchrun, the once-per-replay scalar all-reduce is what the host has to keep up with
+    rounds = int(max(1, min(args.steps // n_rotate, 96 // n_rotate if n_sph <= 128 else 1)))
+    graph_len = rounds * n_rotate
+    graph = graph_of(lambda k: launch(k % n_rotate, stream.cuda_stream), graph_len)
 
     def timed_region(steps):
         """Exactly `steps` steps; returns seconds (device time, this rank)."""
-        reps, rem = divmod(steps, n_rotate)
+        reps, rem = divmod(steps, graph_len)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
@@ -351,7 +355,7 @@ def main():
                     with torch.cuda.stream(comm):
                         dist.all_reduce(energies, op=dist.ReduceOp.SUM, async_op=True)
             for i in range(rem):
-                launch(i, stream.cuda_stream)
+                launch(i % n_rotate, stream.cuda_stream)
             stream.wait_stream(comm)
             ev1.record(stream)
         torch.cuda.synchronize()
@@ -359,7 +363,7 @@ def main():
             dist.barrier()
         return ev0.elapsed_time(ev1) * 1e-3
 
-    timed_region(min(args.steps, 10 * n_rotate))                      # settle clocks / NCCL
+    timed_region(min(args.steps, 3 * graph_len))                      # settle clocks / NCCL
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_local = timed_region(args.steps)
@@ -437,10 +441,36 @@ def main():
 
     e2e_autograd = e2e_scale * timed_e2e(autograd_step, int(min(args.steps, 500)))
 
+    class _Floor(torch.autograd.Function):       # what torch.autograd costs when forward/backward launch nothing
+        @staticmethod
+        def forward(ctx, x, e, g):
+            ctx.g = g
+            return e[0]
+
+        @staticmethod
+        def backward(ctx, go):
+            return ctx.g, None, None
+
+    e_pre, g_pre = torch.zeros(3, device=dev), torch.zeros((n, 3), device=dev)
+
+    def floor_step():
+        tet_v.grad = None
+        with torch.no_grad():
+            tet_v.copy_(x_host, non_blocking=True)
+        e = _Floor.apply(tet_v, e_pre, g_pre)
+        e.backward()
+        g_host.copy_(tet_v.grad, non_blocking=True)
+        e0_host.copy_(e.detach(), non_blocking=True)
+
+    autograd_floor = e2e_scale * timed_e2e(floor_step, int(min(args.steps, 500)))
+
     # ---- extras ------------------------------------------------------------------------------------------
     extras = {"e2e_autograd_surface_iters_per_s": e2e_autograd,
               "e2e_autograd_surface_note": "pinned host x -> H2D -> SmoothnessBarrierEnergy.forward/backward "
                                            "(torch.autograd.Function) -> D2H grad+energy",
+              "e2e_autograd_torch_floor_iters_per_s": autograd_floor,
+              "e2e_autograd_torch_floor_note": "the same step with a torch.autograd.Function that launches nothing: the ceiling "
+                                               "torch's Python autograd machinery and the three copy_ calls leave for this surface",
               "warm_l2_ms_per_step": warm_ms, "warm_l2_iters_per_s": 1e3 / warm_ms,
               "stream_bytes_per_step": int(info["stream_bytes"])}
     if shard_check:
@@ -518,7 +548,7 @@ def main():
                        "l2": f"inputs larger than L2: rotating {n_rotate} distinct packs, {footprint / 1e6:.0f} MB "
                              "of per-step data > 126 MB L2",
                        "grid": int(info["grid"]), "warps_per_cta": int(info["warps_per_cta"]), "segments": int(info["n_segments"]),
-                       "graph": f"CUDA graph of {n_rotate} steps replayed"},
+                       "graph": f"CUDA graph of {graph_len} steps ({rounds} passes over the {n_rotate} packs) replayed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": b_alg, "plan_stream_bytes_per_step": int(info["stream_bytes"]),
@@ -526,7 +556,7 @@ def main():
                                  "the streamed-operator formulation actually moves plan_stream_bytes_per_step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 12),
                     "d2h_bytes_per_step": int(n * 12 + 12), "steps": e2e_steps,
-                    "path": "C-ABI tsb_energy_grad_host: pinned host x -> H2D (copy stream, double-buffered) -> fused launch -> "
+                    "path": "C-ABI tsb_energy_grad_host: pinned host x -> H2D (two alternating internal streams, double-buffered) -> fused launch -> "
                             "D2H grad + energy[3]"},
             "gpu_launches": int(args.steps),
             "clocks": clocks,
