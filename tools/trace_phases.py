@@ -56,10 +56,10 @@ def run(sizes):
                   f"exit spread {tr[:, 11].max() - tr[:, 11].min()} ns; per-CTA total median {np.median(tr[:, 11] - tr[:, 0]):.0f} ns")
             for k, nm in enumerate(names[:d.shape[1]]):
                 print(f"    {nm:18s} median {np.median(d[:, k]):8.0f} ns   max {d[:, k].max():8.0f} ns")
-            ext = np.stack([tr[:, 12] - tr[:, 4], tr[:, 13] - tr[:, 12], tr[:, 14] - tr[:, 13], tr[:, 5] - tr[:, 14]], 1) / 1.965
+            inner = np.stack([tr[:, 12] - tr[:, 4], tr[:, 13] - tr[:, 12], tr[:, 14] - tr[:, 13], tr[:, 5] - tr[:, 14]], 1) / 1.965
             info = tr[:, 15]
             print("    inside rows(w0,seg0): begin-wait / seg setup loads / first RB / other RBs (median ns) = " +
-                  " / ".join(f"{v:.0f}" for v in np.median(ext, 0)) +
+                  " / ".join(f"{v:.0f}" for v in np.median(inner, 0)) +
                   f"; warp0 first RB len4 median {np.median(info & 0xFFFF):.0f}, RBs {np.median((info >> 16) & 0xFF):.0f}, tet cells {np.median((info >> 24) & 0xFF):.0f}")
             post = (tr[:, 9] - tr[:, 3]) / 1.965        # after griddepcontrol.wait -> partial stored
             try:                                         # correlate with the plan (host-side inspection library)
