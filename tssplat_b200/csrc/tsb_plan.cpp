@@ -581,6 +581,20 @@ void emit_tc(std::vector<uint8_t> &s, const Mesh &M, const Comp &C, int t0, int 
 
 }  // namespace
 
+// run fn(begin, end) over [0, count) on up to `nth` threads (contiguous ranges of at least `grain` items)
+template <class F>
+static void parallel_ranges(size_t count, int nth, size_t grain, F fn) {
+  nth = int(std::max<size_t>(1, std::min<size_t>(size_t(std::max(nth, 1)), count / grain + 1)));
+  if (nth == 1) { fn(size_t(0), count); return; }
+  std::vector<std::thread> th;
+  const size_t per = (count + size_t(nth) - 1) / size_t(nth);
+  for (int k = 0; k < nth; ++k) {
+    const size_t b = std::min(count, per * size_t(k)), e = std::min(count, b + per);
+    if (b < e) th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto &t : th) t.join();
+}
+
 int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, const PlanConfig &cfg,
                HostPlan &P, std::string &err) {
   const bool timing = std::getenv("TSSPLAT_B200_PLAN_TIMING") != nullptr;     // developer aid: phase times on stderr
@@ -594,18 +608,39 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   P.nw = cfg.nw;
   const int NW = cfg.nw;
 
-  // ---- validate ----------------------------------------------------------------------------------
-  for (int t = 0; t < nele; ++t) {
-    const int32_t *v = tets + 4 * size_t(t);
-    for (int k = 0; k < 4; ++k)
-      if (v[k] < 0 || v[k] >= n) { err = "tet " + std::to_string(t) + " has a vertex index out of range"; return TSB_E_MESH; }
-    if (v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3]) {
-      err = "tet " + std::to_string(t) + " repeats a vertex"; return TSB_E_MESH;
-    }
-    double Dm[9], Bi[9], det;
-    for (int r = 0; r < 3; ++r)
-      for (int k = 0; k < 3; ++k) Dm[3 * r + k] = double(rest[3 * size_t(v[k + 1]) + r]) - double(rest[3 * size_t(v[0]) + r]);
-    if (!invert3(Dm, Bi, &det) || !std::isfinite(float(1.0 / det))) {
+  // ---- validate (parallel; the lowest offending tet is reported, like a serial scan would) ---------------
+  {
+    const int nth_v = cfg.threads > 0 ? cfg.threads : int(std::thread::hardware_concurrency());
+    std::atomic<int> bad_tet{nele};
+    parallel_ranges(size_t(nele), nth_v, 8192, [&](size_t b, size_t e) {
+      for (size_t t = b; t < e; ++t) {
+        const int32_t *v = tets + 4 * t;
+        bool bad = false;
+        for (int k = 0; k < 4; ++k) bad |= v[k] < 0 || v[k] >= n;
+        if (!bad) {
+          bad = v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3];
+          if (!bad) {
+            double Dm[9], Bi[9], det;
+            for (int r = 0; r < 3; ++r)
+              for (int k = 0; k < 3; ++k) Dm[3 * r + k] = double(rest[3 * size_t(v[k + 1]) + r]) - double(rest[3 * size_t(v[0]) + r]);
+            bad = !invert3(Dm, Bi, &det) || !std::isfinite(float(1.0 / det));
+          }
+        }
+        if (bad) {
+          int cur = bad_tet.load();
+          while (int(t) < cur && !bad_tet.compare_exchange_weak(cur, int(t))) {}
+          return;       // later tets of this range cannot be the lowest
+        }
+      }
+    });
+    if (bad_tet.load() < nele) {
+      const int t = bad_tet.load();
+      const int32_t *v = tets + 4 * size_t(t);
+      for (int k = 0; k < 4; ++k)
+        if (v[k] < 0 || v[k] >= n) { err = "tet " + std::to_string(t) + " has a vertex index out of range"; return TSB_E_MESH; }
+      if (v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3]) {
+        err = "tet " + std::to_string(t) + " repeats a vertex"; return TSB_E_MESH;
+      }
       err = "tet " + std::to_string(t) + " has zero rest volume"; return TSB_E_MESH;
     }
   }
@@ -976,14 +1011,20 @@ int build_plan(const float *rest, const int32_t *tets, int32_t n, int32_t nele, 
   for (const auto &st : wstream) total += st.size();
   if (total / 16 > 0xFFFFFFFFull) { err = "plan stream exceeds 64 GiB"; return TSB_E_NOMEM; }
   P.stream.resize(std::max<size_t>(total, 16));
-  size_t off = 0;
-  for (size_t i = 0; i < wstream.size(); ++i) {
-    const auto &st = wstream[i];
-    if (!st.empty()) std::memcpy(P.stream.data() + off, st.data(), st.size());
-    P.wdesc[2 * i] = uint32_t(off / 16);
-    P.wdesc[2 * i + 1] = uint32_t(st.size());
-    if (st.size() > 0xFFFFFFFFull) { err = "warp stream exceeds 4 GiB"; return TSB_E_NOMEM; }
-    off += st.size();
+  {
+    std::vector<size_t> offs(wstream.size() + 1, 0);
+    for (size_t i = 0; i < wstream.size(); ++i) {
+      if (wstream[i].size() > 0xFFFFFFFFull) { err = "warp stream exceeds 4 GiB"; return TSB_E_NOMEM; }
+      P.wdesc[2 * i] = uint32_t(offs[i] / 16);
+      P.wdesc[2 * i + 1] = uint32_t(wstream[i].size());
+      offs[i + 1] = offs[i] + wstream[i].size();
+    }
+    const int nth_c = cfg.threads > 0 ? cfg.threads : int(std::thread::hardware_concurrency());
+    uint8_t *dst = P.stream.data();
+    parallel_ranges(wstream.size(), total > (size_t(8) << 20) ? std::min(nth_c, 32) : 1, 16, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i)
+        if (!wstream[i].empty()) std::memcpy(dst + offs[i], wstream[i].data(), wstream[i].size());
+    });
   }
   TSB_T("concat");
   return TSB_OK;

@@ -39,7 +39,10 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace tsb {
@@ -84,6 +87,17 @@ struct PlanConfig {
   int32_t enable_amips = 0;     // also emit the per-tet rest inverses (AMIPS term; 48 B per tet)
 };
 
+// std::allocator whose construct() default-initialises: resize() of a byte vector does not zero-fill
+// (the 306 MB stream of a 1024-sphere plan is first touched by the parallel copies that fill it)
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+
 struct HostPlan {
   int32_t n = 0, nele = 0, n_components = 0, n_boundary_faces = 0, laplacian_scale = 0;
   int32_t mode_global = 0;      // 0 = STAGED, 1 = GLOBAL
@@ -98,7 +112,7 @@ struct HostPlan {
   int64_t gather_wavefronts[2] = {0, 0};   // STAGED row gathers: (wavefronts, ideal) per quarter-warp and slot
   int64_t tet_wavefronts[2] = {0, 0};
 
-  std::vector<uint8_t> stream;      // all warp streams, 16-byte aligned
+  std::vector<uint8_t, NoInitAlloc<uint8_t>> stream;   // all warp streams, 16-byte aligned (filled by parallel copies)
   std::vector<float> X4;            // 4 floats per staged vertex (X, Y, Z, 0), component-major
   std::vector<int32_t> vlist;       // global id per staged vertex (same order as X4)
   // Bank-aware placement: vertex k of a component is staged at position pos16[x4off + k] of its u / x
