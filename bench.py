@@ -288,14 +288,16 @@ def main():
         n_sph = args.spheres_per_gpu
     total_spheres = args.total_spheres if strong else n_sph * world
     c1, c2 = 2e-4 / total_spheres, 2e-4
-    packs, handles, xs = [], [], []
+    packs, handles, xs, create_main = [], [], [], []
     L2_BYTES = 126e6
     n_rotate = None
     i = 0
     while n_rotate is None or i < n_rotate:
         pk = make_pack(n_sph, TETS, seed=1000 * rank + 17 * i, unique=8)
         packs.append(pk)
+        t_c = time.perf_counter()
         handles.append(ext.TetSpheres(pk.verts.reshape(-1), pk.tets.reshape(-1)))
+        create_main.append(time.perf_counter() - t_c)
         xs.append(torch.from_numpy(perturb(pk, sigma_rel=0.02, seed=i)).to(dev))
         if n_rotate is None:   # enough distinct packs that one rotation streams > 1.5 x L2 through the GPU
             n_rotate = int(min(64, max(2, -(-1.5 * L2_BYTES // handles[0].info["stream_bytes"]))))
@@ -471,16 +473,24 @@ def main():
               "e2e_autograd_torch_floor_iters_per_s": autograd_floor,
               "e2e_autograd_torch_floor_note": "the same step with a torch.autograd.Function that launches nothing: the ceiling "
                                                "torch's Python autograd machinery and the three copy_ calls leave for this surface",
+              "tsb_create_seconds_64_spheres": float(np.median(create_main)),
+              "tsb_create_note": "setup (SURVEY 8 f3): host plan build on all cores + upload, median over the rotating packs; "
+                                 "the 1024-sphere figure is in config4_1024_spheres_one_gpu",
               "warm_l2_ms_per_step": warm_ms, "warm_l2_iters_per_s": 1e3 / warm_ms,
               "stream_bytes_per_step": int(info["stream_bytes"])}
     if shard_check:
         extras["sharded_path_check"] = shard_check
     peak, peak_src = _peaks()
 
+    create_s = {}
+
     def one_pack_rate(S, seed):
         """us/step of one S-sphere pack on this GPU (graph replay; > L2 when S >= 512)."""
         pk = make_pack(S, TETS, seed=seed, unique=8)
+        t_c = time.perf_counter()
         h = ext.TetSpheres(pk.verts.reshape(-1), pk.tets.reshape(-1))
+        torch.cuda.synchronize()
+        create_s[S] = time.perf_counter() - t_c
         xx = [torch.from_numpy(perturb(pk, sigma_rel=0.02, seed=0)).to(dev)]
         en = torch.zeros((1, 3), device=dev)
         gr = [torch.empty((h.n, 3), device=dev)]
@@ -498,6 +508,7 @@ def main():
             extras["config4_1024_spheres_one_gpu"] = {"us_per_step": sec * 1e6, "algorithmic_GBps": b1k / sec / 1e9,
                                                       "hbm_frac_by_B_alg": b1k / sec / 1e9 / peak,
                                                       "plan_stream_GBps": inf["stream_bytes"] / sec / 1e9,
+                                                      "tsb_create_seconds": create_s.get(1024),
                                                       "note": "BASELINE configs[4] pack (1024 spheres, 4.2 M tets) on ONE GPU: "
                                                               "306 MB of plan data per step, HBM-streaming regime"}
             try:
