@@ -171,6 +171,19 @@ int tsb_surface_forward(tsb_surface_t s, const float *tet_v_dev, float *v_pos_de
 int tsb_surface_backward(tsb_surface_t s, const float *tet_v_dev, const float *grad_v_pos_dev,
                          const float *grad_v_nrm_dev, float *grad_tet_v_dev, void *stream);
 
+/* ---- "Next" row (f)3: surface extraction on the GPU --------------------------------------------------------
+ * Replaces get_surface_vf (geometry/mesh_utils.py:5-35; re-run by reset() / permute_surface_v(),
+ * geometry/tetmesh_geometry.py:164-170,369-371) with identical output: the faces that belong to exactly one tet, in
+ * lexicographic order of their sorted vertex triple, each in the orientation its tet gives it (face k opposite local
+ * vertex k: (1,2,3), (0,3,2), (0,1,3), (0,2,1)), re-indexed into the increasing list of surface vertex ids.
+ * tets_host: host int32 [4*nele], 0-based, entries in [0, n).  On success *surface_vid_out (int32 [*nsv_out]) and
+ * *surface_f_out (int32 [3 * *nsf_out]) are host arrays owned by the caller: release them with tsb_free_host.
+ * Synchronous (a setup call); errors are reported through tsb_setup_last_error (thread-local). */
+int tsb_surface_extract(const int32_t *tets_host, int32_t nele, int32_t n, int device, int32_t *nsv_out,
+                        int32_t *nsf_out, int32_t **surface_vid_out, int32_t **surface_f_out);
+void tsb_free_host(void *p);
+const char *tsb_setup_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -489,3 +489,29 @@ def test_handles_with_different_staging_sizes_coexist(ext):
     e, g = a.energy_grad(xa, 1e-4, 2e-4, 2)
     eo, _, go = COracle(big.verts, big.tets).energy_grad(xa.cpu().numpy(), 1e-4, 2e-4, 2)
     assert float(e[0]) == pytest.approx(eo, rel=REL) and np.linalg.norm(g.cpu().numpy() - go) <= REL * np.linalg.norm(go)
+
+
+def test_surface_extraction_on_gpu_matches_reference(ext):
+    """tsb_surface_extract (radix sorts + select + scan on the device) against fixtures produced by the reference's own
+    get_surface_vf (geometry/mesh_utils.py:5-35, via tests/golden/make_ref_fixtures.py) and against the numpy
+    restatement: identical vertex list, identical triangles in identical order and orientation."""
+    from tssplat_b200.mesh import surface_vf, surface_vf_gpu
+    fix = np.load(os.path.join(GOLDEN, "ref_fixtures.npz"))
+    d = np.load(os.path.join(GOLDEN, "a_veg_mesh.npz"))
+    pk = make_pack(3, 1024, seed=1)
+    for name, t in {"a_veg": d["tets"], "pack3x1024": pk.tets}.items():
+        sv, sf = surface_vf_gpu(t)
+        assert np.array_equal(sv, fix[name + "/surface_vid"]) and np.array_equal(sf, fix[name + "/surface_f"])
+    # a large pack (64 x 4096), unused vertex ids, a face shared by three tets (dropped like the reference drops it)
+    big = make_pack(64, 4096, seed=3, unique=4)
+    sv, sf = surface_vf_gpu(big.tets, big.n)
+    sv0, sf0 = surface_vf(big.tets)
+    assert np.array_equal(sv, sv0) and np.array_equal(sf, sf0)
+    odd = np.array([[0, 1, 2, 3], [0, 1, 2, 4], [0, 1, 2, 9], [5, 6, 7, 9]], dtype=np.int32)
+    sv, sf = surface_vf_gpu(odd, 12)
+    sv0, sf0 = surface_vf(odd)
+    assert np.array_equal(sv, sv0) and np.array_equal(sf, sf0)
+    sv, sf = surface_vf_gpu(np.zeros((0, 4), dtype=np.int32), 5)
+    assert len(sv) == 0 and sf.shape == (0, 3)
+    with pytest.raises(RuntimeError, match="out of range"):
+        surface_vf_gpu(np.array([[0, 1, 2, 7]], dtype=np.int32), 4)

@@ -13,8 +13,10 @@ from tssplat_b200 import tet_spheres_ext as ext  # noqa: E402
 from tssplat_b200.mesh import make_pack, perturb  # noqa: E402
 
 S, NH, NX = 64, 9, 220
+KW = {"warps_per_cta": 8, "ring_slots": 2} if len(sys.argv) > 1 and sys.argv[1] == "nw8" else {}
 pack = make_pack(S, 4096, seed=0, unique=8)
-hs = [ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1)) for _ in range(NH)]
+hs = [ext.TetSpheres(pack.verts.reshape(-1), pack.tets.reshape(-1), **KW) for _ in range(NH)]
+print(KW, {k: hs[0].info[k] for k in ("grid", "warps_per_cta", "ctas_per_sm", "smem_bytes", "ring_slots")})
 x0 = torch.from_numpy(perturb(pack, sigma_rel=0.02, seed=0)).cuda()
 xs = [x0.clone() for _ in range(NX)]
 gs = [torch.empty_like(x0) for _ in range(NX)]
@@ -47,7 +49,7 @@ def run(label, hsel, xsel, count):
     print(f"  {label}: {e0.elapsed_time(e1) * 1e3 / (reps * count):.2f} us/step", flush=True)
 
 
-for _ in range(2):
+for _ in range(1):
     run("A all warm                 ", lambda k: 0, lambda k: 0, 90)
     run("B plan cold (9 handles)    ", lambda k: k % NH, lambda k: 0, 90)
     run("C x/grad cold (220 buffers)", lambda k: 0, lambda k: k % NX, NX)

@@ -48,4 +48,8 @@ if not big:
     (v_pos.sum() + (v_nrm * v_nrm).sum()).backward()
     torch.cuda.synchronize()
     print("helpers ok", float(tv.grad.abs().sum()))
+    from tssplat_b200.mesh import surface_vf_gpu
+    sv2, sf2 = surface_vf_gpu(pack.tets, pack.n)
+    assert np.array_equal(sv, sv2) and np.array_equal(sf, sf2)
+    print("surface extraction ok", len(sv2), len(sf2))
 print("DONE")

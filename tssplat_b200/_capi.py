@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "tsb_create", "tsb_destroy", "tsb_last_error", "tsb_get_info", "tsb_energy_grad", "tsb_energy_grad_ex", "tsb_energy_grad_host", "tsb_scale",
     "tsb_grad_limit", "tsb_adam_uniform_step",
     "tsb_surface_create", "tsb_surface_destroy", "tsb_surface_last_error", "tsb_surface_forward", "tsb_surface_backward",
+    "tsb_surface_extract", "tsb_free_host", "tsb_setup_last_error",
 )
 
 
@@ -82,6 +83,13 @@ def _load() -> C.CDLL:
     lib.tsb_surface_forward.argtypes = [vp, vp, vp, vp, vp]
     lib.tsb_surface_backward.restype = C.c_int
     lib.tsb_surface_backward.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.tsb_surface_extract.restype = C.c_int
+    lib.tsb_surface_extract.argtypes = [vp, C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]
+    lib.tsb_free_host.restype = None
+    lib.tsb_free_host.argtypes = [vp]
+    lib.tsb_setup_last_error.restype = C.c_char_p
+    lib.tsb_setup_last_error.argtypes = []
     return lib
 
 

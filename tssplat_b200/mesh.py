@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 __all__ = ["TetPack", "load_veg", "save_veg", "make_tet_sphere", "make_pack", "concat_spheres",
-           "perturb", "mean_edge_length", "connected_components", "surface_vf", "save_npy_spheres",
+           "perturb", "mean_edge_length", "connected_components", "surface_vf", "surface_vf_gpu", "save_npy_spheres",
            "load_npy_spheres"]
 
 _EDGES = np.array([[0, 1], [0, 2], [0, 3], [1, 2], [1, 3], [2, 3]])
@@ -261,6 +261,30 @@ def surface_vf(tets: np.ndarray):
     faces = oriented[order[once]]
     verts = np.unique(faces)
     return verts, np.searchsorted(verts, faces)
+
+
+def surface_vf_gpu(tets: np.ndarray, n_vertices: Optional[int] = None, device: int = 0):
+    """``surface_vf`` on the GPU (``tsb_surface_extract``: two radix sorts, a select and a scan): the same
+    ``(surface_vertices, surface_triangles)`` as the reference's ``get_surface_vf``
+    (``geometry/mesh_utils.py:5-35``), for ``reset()`` / ``permute_surface_v()``-style re-runs on large packs.
+    Needs a CUDA device (no CPU path: use ``surface_vf`` for the numpy restatement)."""
+    import ctypes as C
+
+    from . import _capi
+    t = np.ascontiguousarray(np.asarray(tets).reshape(-1, 4), dtype=np.int32)
+    n = int(n_vertices) if n_vertices is not None else (int(t.max()) + 1 if t.size else 0)
+    nsv, nsf = C.c_int32(0), C.c_int32(0)
+    pv, pf = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+    rc = _capi.lib.tsb_surface_extract(t.ctypes.data, len(t), n, int(device), C.byref(nsv), C.byref(nsf), C.byref(pv), C.byref(pf))
+    if rc:
+        raise RuntimeError(f"surface_vf_gpu: {(_capi.lib.tsb_setup_last_error() or b'').decode()} (code {rc})")
+    try:
+        verts = np.ctypeslib.as_array(pv, shape=(nsv.value,)).astype(np.int64) if nsv.value else np.zeros(0, np.int64)
+        faces = np.ctypeslib.as_array(pf, shape=(nsf.value, 3)).astype(np.int64) if nsf.value else np.zeros((0, 3), np.int64)
+    finally:
+        _capi.lib.tsb_free_host(pv)
+        _capi.lib.tsb_free_host(pf)
+    return verts, faces
 
 
 def save_npy_spheres(pack: "TetPack", path: str, filename: str, verts: Optional[np.ndarray] = None) -> List[str]:
