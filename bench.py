@@ -43,8 +43,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-os.environ.setdefault("OMP_PROC_BIND", "close")      # CPU arms: pin the OpenMP threads (set before libgomp loads)
-os.environ.setdefault("OMP_PLACES", "cores")
+if "reference" in sys.argv:       # CPU arm only: pin the OpenMP threads (must be set before libgomp loads).  The GPU arm runs
+    os.environ.setdefault("OMP_PROC_BIND", "close")     # its cpu_baseline leg in a child process instead: binding would
+    os.environ.setdefault("OMP_PLACES", "cores")        # confine this process (and the plan builder's threads) to one core
 
 SPHERES, TETS = 64, 4096
 METRIC = "geometry_energy_grad_iters_per_sec_64x4k"
@@ -197,7 +198,7 @@ def run_reference(args):
     dt0, variant, cores, co = _calibrate(pack, x, c1, c2)
     for _ in range(max(args.warmup, 3)):
         co.energy_grad(x, c1, c2, ORDER, nthreads=cores)
-    ts = _time_cpu(co, x, c1, c2, cores, min_seconds=2.0, min_steps=max(200, min(args.steps, 2000)))
+    ts = _time_cpu(co, x, c1, c2, cores, min_seconds=args.min_seconds, min_steps=max(200, min(args.steps, 2000)))
     dt = float(np.median(ts))
     value = 1.0 / dt
     sample = (f"{len(ts)} energy+gradient iterations of the full {SPHERES}-sphere pack ({SPHERES * TETS} tets), median step time "
@@ -230,6 +231,7 @@ def main():
     ap.add_argument("--total-spheres", type=int, default=0,
                     help="strong scaling: total spheres split sphere-per-rank (BASELINE configs[3], [4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="CPU arm: minimum timed duration")
     ap.add_argument("--no-extras", action="store_true", help="skip the size sweep / trainer-loop / strong-scaling extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -575,14 +577,15 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline and n_sph == SPHERES:
             x0 = xs[0].cpu().numpy()
-            dt0, variant, cores, co = _calibrate(packs[0], x0, c1, c2)
-            ts = _time_cpu(co, x0, c1, c2, cores, min_seconds=10.0, min_steps=200)
-            tc = float(np.median(ts))
-            out["cpu_baseline"] = {"value": 1.0 / tc, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"{len(ts)} energy+gradient iterations of the full 64-sphere pack, median step "
-                                             f"(p10 {np.percentile(ts, 10) * 1e3:.2f} ms, p90 {np.percentile(ts, 90) * 1e3:.2f} ms); "
-                                             f"matrix-free C port (oracle/tet_energy_oracle.c), {_variant_name(variant)}, OpenMP "
-                                             f"{cores} threads pinned (fastest of the builds/thread counts tried, {_host_threads()} available)"}
+            # the CPU port, timed in a child process (pinned OpenMP threads, all host cores): `--impl reference` itself
+            import subprocess
+            env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS",)}
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--min-seconds", "10"],
+                               capture_output=True, text=True, env=env, timeout=600)
+            try:
+                out["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                raise RuntimeError("cpu_baseline leg failed: " + r.stderr[-2000:])
             if not args.no_extras:
                 # the reference-shaped "vanilla PyTorch" pipeline (SpMV GTLTLG, SpMV G, autograd), best thread count
                 from oracle.torch_energy import time_fwd_bwd

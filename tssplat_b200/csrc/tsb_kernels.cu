@@ -187,8 +187,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
   float px[SV][3];
   float4 pX[SV];                    // rest position; .w carries the staging position (bit pattern)
   bool pre = false;                 // (px, pX) hold a prefetched component
+  SegHdr h1{};                      // second segment's header (plan data: fetched before the wait as well)
   if (cs.x < cs.y) {
     hcur = p.segs[cs.x];
+    if (!GLOBAL && cs.x + 1 < cs.y) h1 = p.segs[cs.x + 1];
     if (!GLOBAL && !hcur.whole) {   // rest positions of the first component: plan data, loaded before the wait
 #pragma unroll
       for (int k = 0; k < SV; ++k) {
@@ -256,11 +258,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
   bool eager2 = false;
   if (!GLOBAL) {
     if (cs.x < cs.y) {
-      SegHdr h1{};
-      if (cs.x + 1 < cs.y && !hcur.whole) {
-        h1 = p.segs[cs.x + 1];
-        eager2 = !h1.whole;
-      }
+      if (cs.x + 1 < cs.y && !hcur.whole) eager2 = !h1.whole;
       if (hcur.whole) {
         stage_direct(hcur, 0);
       } else if (!eager2) {
@@ -560,17 +558,38 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
   if (blockIdx.x == 0 && warp == 0) {
     __syncwarp();
     double a = 0.0, b = 0.0, c3sum = 0.0;
-    for (int c = lane; c < int(gridDim.x); c += 32) {
-      unsigned long long ua, ub, uc, ud;
-      do {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(p.cta_energy + 4 * c) : "memory");
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(uc), "=l"(ud) : "l"(p.cta_energy + 4 * c + 2) : "memory");
-      } while (ua == kSentinel || ub == kSentinel || uc == kSentinel || ud == kSentinel);
-      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c), "l"(kSentinel), "l"(kSentinel) : "memory");   // re-arm
-      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c + 2), "l"(kSentinel), "l"(kSentinel) : "memory");
-      a += __longlong_as_double((long long)ua);
-      b += __longlong_as_double((long long)ub);
-      c3sum += __longlong_as_double((long long)uc);
+    // Each lane owns slots lane, lane + 32, ...; the loads of a batch of kPollBatch slots are issued together, so one
+    // L2 round trip after the last partial has landed finishes the fold (polling them one after the other cost five
+    // dependent round trips, ~2 us per launch).  The summation order stays fixed: slot order per lane, then the shuffle tree.
+    constexpr int kPollBatch = 5;
+    for (int c0 = lane; c0 < int(gridDim.x); c0 += 32 * kPollBatch) {
+      unsigned long long ua[kPollBatch], ub[kPollBatch], uc[kPollBatch], ud[kPollBatch];
+      bool pending = true;
+      while (pending) {
+        pending = false;
+#pragma unroll
+        for (int k = 0; k < kPollBatch; ++k) {
+          const int c = c0 + 32 * k;
+          if (c < int(gridDim.x)) {
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua[k]), "=l"(ub[k]) : "l"(p.cta_energy + 4 * c) : "memory");
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(uc[k]), "=l"(ud[k]) : "l"(p.cta_energy + 4 * c + 2) : "memory");
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kPollBatch; ++k)
+          if (c0 + 32 * k < int(gridDim.x)) pending |= ua[k] == kSentinel || ub[k] == kSentinel || uc[k] == kSentinel || ud[k] == kSentinel;
+      }
+#pragma unroll
+      for (int k = 0; k < kPollBatch; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < int(gridDim.x)) {
+          asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c), "l"(kSentinel), "l"(kSentinel) : "memory");   // re-arm
+          asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p.cta_energy + 4 * c + 2), "l"(kSentinel), "l"(kSentinel) : "memory");
+          a += __longlong_as_double((long long)ua[k]);
+          b += __longlong_as_double((long long)ub[k]);
+          c3sum += __longlong_as_double((long long)uc[k]);
+        }
+      }
     }
     a = warp_sum(a); b = warp_sum(b); c3sum = warp_sum(c3sum);
     if (lane == 0) {
