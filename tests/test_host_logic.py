@@ -252,3 +252,26 @@ def test_drop_in_import_and_scheduler():
     m = 2 ** (4 * abs(math.sin(600 / 2400 * math.pi)))
     assert c1 == pytest.approx(2e-4 / 64 * m) and c2 == pytest.approx(2e-4 * m)
     assert eng.coeff_scheduler(5000) == pytest.approx((2e-4 / 64 * 16, 2e-4 * 16))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys, the same metric/unit as the GPU arm, e2e == value with zero copy bytes, no GPU launches.  Under torchrun only
+    rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3", "--min-seconds", "0.2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+              "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "geometry_energy_grad_iters_per_sec_64x4k" and d["unit"] == "iters/s"
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["steps"] >= 200
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""

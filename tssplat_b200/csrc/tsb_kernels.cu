@@ -513,22 +513,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) energy_grad_kernel(const KParam
     if (s == cs.x) TSB_STAMP(6);
 
     // ---- hand the staging buffers over ------------------------------------------------------------------
-    if (!GLOBAL) {
-      if (li == 0 && eager2) {
-        // segment 1 is already staged: no barrier
-      } else {
-        if (pre) {
-          if (li == 1 && eager2) __syncthreads();     // half 0 is reused: every warp must have left segment 0
-          store_staged(hn, li + 1);
-        }
-        __syncthreads();
-        if (s + 1 < cs.y && !pre) {
-          stage_direct(hn, li + 1);
+    if (s + 1 < cs.y) {      // (after the last segment the energy fold's own barrier is the only one needed)
+      if (!GLOBAL) {
+        if (li == 0 && eager2) {
+          // segment 1 is already staged: no barrier
+        } else {
+          if (pre) {
+            if (li == 1 && eager2) __syncthreads();     // half 0 is reused: every warp must have left segment 0
+            store_staged(hn, li + 1);
+          }
           __syncthreads();
+          if (!pre) {
+            stage_direct(hn, li + 1);
+            __syncthreads();
+          }
         }
+      } else if (grad) {
+        __syncthreads();     // keeps the named barrier's generations apart
       }
-    } else if (grad) {
-      __syncthreads();     // keeps the named barrier's generations apart
     }
     hcur = hn;
   }
