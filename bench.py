@@ -485,6 +485,7 @@ def main():
     peak, peak_src = _peaks()
 
     create_s = {}
+    extras_1sphere_us = None
 
     def one_pack_rate(S, seed):
         """us/step of one S-sphere pack on this GPU (graph replay; > L2 when S >= 512)."""
@@ -503,6 +504,8 @@ def main():
 
     if not args.no_extras and not strong and n_sph == SPHERES:
         if world == 1:
+            sec1, _, _ = one_pack_rate(1, 7000)
+            extras_1sphere_us = sec1 * 1e6
             sec, b16, _ = one_pack_rate(16, 7001)
             extras["config1_16_spheres"] = {"us_per_step": sec * 1e6, "iters_per_s": 1.0 / sec, "hbm_frac_by_B_alg": b16 / sec / 1e9 / peak,
                                             "note": "BASELINE configs[1]: 16 tet-spheres, fused kernel only, fp32, 1 GPU (L2-resident)"}
@@ -596,6 +599,16 @@ def main():
                     tt_, _, _ = time_fwd_bwd(sub.verts, sub.tets, x0[:v1], c1, c2, ORDER, iters=4, warmup=1, threads=th)
                     if best is None or tt_ < best[0]:
                         best = (tt_, th)
+                # BASELINE configs[0]: ONE tet-sphere, vanilla-PyTorch forward+backward on the host cores, beside the fused
+                # launch on the same sphere
+                one = packs[0].slice_spheres(0, 1)
+                v0 = int(packs[0].vert_offsets[1])
+                t1s, _, _ = time_fwd_bwd(one.verts, one.tets, x0[:v0], c1, c2, ORDER, iters=10, warmup=2, threads=best[1])
+                out["extras"]["config0_1_sphere"] = {
+                    "vanilla_torch_cpu_ms_per_fwd_bwd": t1s * 1e3, "threads": best[1],
+                    "b200_fused_launch_us": extras_1sphere_us,
+                    "note": "BASELINE configs[0]: 1 tet-sphere x 4096 tets; torch sparse fp32 + autograd restatement of the "
+                            "reference's SpMV pipeline on the CPU vs ONE fused energy+grad launch (graph replay)"}
                 out["extras"]["cpu_torch_restatement_iters_per_s"] = 1.0 / (best[0] * SPHERES / ns)
                 out["extras"]["cpu_torch_restatement_note"] = (f"torch sparse fp32 + autograd restatement of the reference's SpMV "
                                                                f"pipeline, {ns} of {SPHERES} spheres extrapolated, best of thread "
