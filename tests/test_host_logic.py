@@ -275,3 +275,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_autograd_bridge_builds_and_binds():
+    """The C++ autograd bridge (csrc/torch_binding.cpp) compiles with the image's g++ against this torch, loads, and
+    takes the C entry points from the already loaded library (no GPU needed for any of that)."""
+    from tssplat_b200 import native_autograd
+    so = native_autograd.build()
+    assert so and os.path.exists(so)
+    assert native_autograd.available()
+    mod = native_autograd.module()
+    for name in ("bind", "state_new", "state_free", "note_parameters_changed", "energy"):
+        assert hasattr(mod, name)
+    mod.note_parameters_changed()

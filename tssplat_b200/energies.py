@@ -18,6 +18,11 @@ from tet_spheres import tet_spheres_ext
 __all__ = ["SmoothnessBarrierFunc", "SmoothnessBarrierEnergy"]
 
 
+#: route SmoothnessBarrierEnergy through the C++ autograd bridge when it has been built (same launches, same
+#: semantics, no Python between autograd and the C ABI); False forces the Python Function below
+use_native_autograd = True
+
+
 class SmoothnessBarrierFunc(torch.autograd.Function):
     """autograd bridge (``energies/smooth_barrier.py:9-31``): forward returns the 0-dim energy,
     backward returns ``(dE/dx * grad_output, None, None, None, None)`` and short-circuits on a
@@ -63,4 +68,9 @@ class SmoothnessBarrierEnergy(torch.nn.Module):
 
     def forward(self, x, it, c1, c2):
         order = 4 if it > self.FLAGS.increase_order_iter else 2     # smooth_barrier.py:61-63
+        if (use_native_autograd and self.smooth_eng_func is SmoothnessBarrierFunc and tet_spheres_ext.fuse_backward_into_forward
+                and not tet_spheres_ext.return_cpu_scalar):
+            ns = self.tet_sp.native_state()        # C++ torch::autograd::Function over the same C ABI (csrc/torch_binding.cpp)
+            if ns is not None:
+                return ns[0].energy(x, ns[1], float(c1), float(c2), order)
         return self.smooth_eng_func.apply(x, self.tet_sp, c1, c2, order)

@@ -111,11 +111,29 @@ class TetSpheres:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
+        ns, self._native = getattr(self, "_native", None), None
+        if ns:
+            try:
+                ns[0].state_free(ns[1])
+            except Exception:  # interpreter shutdown
+                pass
         if h:
             try:
                 _capi.lib.tsb_destroy(h)
             except Exception:  # interpreter shutdown
                 pass
+
+    def native_state(self):
+        """(module, state) of the C++ autograd bridge for this handle, or None when it is not built
+        (``tssplat_b200.native_autograd``)."""
+        ns = getattr(self, "_native", None)
+        if ns is None:
+            from . import native_autograd
+            mod = native_autograd.module()
+            if mod is None:
+                return None
+            ns = self._native = (mod, mod.state_new(int(self._h.value), self.n, int(self.device.index)))
+        return ns
 
     # ------------------------------------------------------------------------------------------
     def _check_x(self, x: torch.Tensor) -> torch.Tensor:
@@ -186,6 +204,10 @@ def note_parameters_changed() -> None:
     """Tell the fused-gradient cache that vertex positions were modified in place behind autograd's back."""
     global _mutation_epoch
     _mutation_epoch += 1
+    from . import native_autograd
+    mod = native_autograd.module()
+    if mod is not None:
+        mod.note_parameters_changed()
 
 
 def _key(x: torch.Tensor, c1, c2, order):
