@@ -537,7 +537,7 @@ def test_native_autograd_bridge_matches_python_function(ext):
                 x = torch.from_numpy(x_np).cuda().requires_grad_(True)
                 e = eng(x, it, 1e-4, 2e-4)
                 (e * 0.5).backward()                                  # CUDA grad_output 0.5
-                res[native] = (float(e), x.grad.clone())
+                res[native] = (float(e.detach()), x.grad.clone())
             assert res[True][0] == res[False][0]
             assert (res[True][1] - res[False][1]).norm() <= 1e-6 * res[False][1].norm()
             eo, _, go = oracle.energy_grad(x_np, 1e-4, 2e-4, order, gradH=0.5)
