@@ -565,5 +565,15 @@ def test_native_autograd_bridge_matches_python_function(ext):
         # errors surface as exceptions
         with pytest.raises(RuntimeError):
             eng(torch.zeros(5, device="cuda", requires_grad=True), 0, 1e-4, 2e-4)
+        # the graph keeps the handle alive: backward after the energy module is gone
+        import gc
+        eng2 = energies.SmoothnessBarrierEnergy(pack.verts, pack.tets, dict(smooth_eng_coeff=1e-4, barrier_coeff=2e-4, increase_order_iter=10))
+        x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+        loss = eng2(x, 0, 1e-4, 2e-4) * 3.0
+        del eng2
+        gc.collect()
+        loss.backward()
+        _, _, go = oracle.energy_grad(x_np, 1e-4, 2e-4, 2, gradH=3.0)
+        assert np.linalg.norm(x.grad.cpu().numpy() - go) <= REL * np.linalg.norm(go)
     finally:
         energies.use_native_autograd = True

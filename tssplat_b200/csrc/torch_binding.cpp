@@ -36,6 +36,22 @@ struct State {
   int64_t ring_i = 0;
 };
 
+// keeps a Python object alive from inside an autograd node (IValue payload); released under the GIL
+struct OwnerHolder final : c10::ivalue::PyObjectHolder {
+  explicit OwnerHolder(py::object o) : obj(std::move(o)) {}
+  PyObject *getPyObject() override { return obj.ptr(); }
+  c10::InferredType tryToInferType() override { return c10::InferredType("tssplat_b200 owner object"); }
+  c10::IValue toIValue(const c10::TypePtr &, std::optional<int32_t>) override { TORCH_CHECK(false, "not convertible"); }
+  std::string toStr() override { return "tssplat_b200.TetSpheres"; }
+  std::vector<at::Tensor> extractTensors() override { return {}; }
+  ~OwnerHolder() override {
+    py::gil_scoped_acquire gil;
+    obj.dec_ref();
+    obj.ptr() = nullptr;
+  }
+  py::object obj;
+};
+
 void check(int rc, const State *S, const char *what) {
   if (rc == TSB_OK) return;
   const char *msg = g_last_error ? g_last_error(S ? S->h : nullptr) : "";
@@ -70,9 +86,12 @@ std::pair<torch::Tensor, torch::Tensor> launch(State *S, const torch::Tensor &x,
 }
 
 struct EnergyFunction : public torch::autograd::Function<EnergyFunction> {
+  // `owner`: the Python TetSpheres that owns `state` and the C handle; the graph node keeps it alive (like
+  // ctx.constants does on the Python route), so a backward that outlives the energy module stays valid
   static torch::Tensor forward(torch::autograd::AutogradContext *ctx, const torch::Tensor &x, int64_t state, double c1, double c2,
-                               int64_t order) {
+                               int64_t order, const py::object &owner) {
     State *S = reinterpret_cast<State *>(state);
+    ctx->saved_data["owner"] = c10::IValue(c10::intrusive_ptr<c10::ivalue::PyObjectHolder>(c10::make_intrusive<OwnerHolder>(owner)));
     const bool want = x.requires_grad();
     auto eg = launch(S, x, c1, c2, order, 1.f, nullptr, want);
     ctx->save_for_backward({x});
@@ -89,7 +108,7 @@ struct EnergyFunction : public torch::autograd::Function<EnergyFunction> {
 
   static torch::autograd::tensor_list backward(torch::autograd::AutogradContext *ctx, torch::autograd::tensor_list grad_outputs) {
     const torch::Tensor &go = grad_outputs[0];
-    if (!go.defined()) return {torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor()};
+    if (!go.defined()) return {torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor()};
     State *S = reinterpret_cast<State *>(ctx->saved_data["state"].toInt());
     const auto saved = ctx->get_saved_variables();
     const torch::Tensor &x = saved[0];
@@ -118,7 +137,7 @@ struct EnergyFunction : public torch::autograd::Function<EnergyFunction> {
     } else {
       g = launch(S, x, c1, c2, order, gh, go_dev.defined() ? go_dev.data_ptr<float>() : nullptr, true).second;
     }
-    return {g.view(x.sizes()), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor()};
+    return {g.view(x.sizes()), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor(), torch::Tensor()};
   }
 };
 
@@ -142,7 +161,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("state_free", [](int64_t state) { delete reinterpret_cast<State *>(state); });
   m.def("note_parameters_changed", []() { g_epoch.fetch_add(1); });
-  m.def("energy", [](const torch::Tensor &x, int64_t state, double c1, double c2, int64_t order) {
-    return EnergyFunction::apply(x, state, c1, c2, order);
-  }, "differentiable E(x) as a 0-dim tensor on x's device (SmoothnessBarrierFunc.apply)");
+  m.def("energy", [](const torch::Tensor &x, int64_t state, double c1, double c2, int64_t order, const py::object &owner) {
+    return EnergyFunction::apply(x, state, c1, c2, order, owner);
+  }, "differentiable E(x) as a 0-dim tensor on x's device (SmoothnessBarrierFunc.apply); `owner` is kept alive by the graph");
 }

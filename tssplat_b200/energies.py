@@ -72,5 +72,5 @@ class SmoothnessBarrierEnergy(torch.nn.Module):
                 and not tet_spheres_ext.return_cpu_scalar):
             ns = self.tet_sp.native_state()        # C++ torch::autograd::Function over the same C ABI (csrc/torch_binding.cpp)
             if ns is not None:
-                return ns[0].energy(x, ns[1], float(c1), float(c2), order)
+                return ns[0].energy(x, ns[1], float(c1), float(c2), order, self.tet_sp)
         return self.smooth_eng_func.apply(x, self.tet_sp, c1, c2, order)
