@@ -288,3 +288,51 @@ def test_native_autograd_bridge_builds_and_binds():
     for name in ("bind", "state_new", "state_free", "note_parameters_changed", "energy"):
         assert hasattr(mod, name)
     mod.note_parameters_changed()
+
+
+def _ragged_mesh(rng, n_comp, max_tets):
+    """Components = connected chunks of tet-spheres (ragged boundaries), vertex ids shuffled over a range with
+    gaps (unreferenced vertices), tets of different components interleaved."""
+    verts, tets = [], []
+    for c in range(n_comp):
+        v, t = make_tet_sphere(1300 + int(rng.integers(0, 50)), int(rng.integers(24, max_tets)))
+        keep = t[: int(rng.integers(max(4, len(t) // 3), len(t) + 1))]          # a prefix of the generator's order stays face-connected
+        used = np.unique(keep)
+        remap = -np.ones(len(v), dtype=np.int64)
+        remap[used] = np.arange(len(used))
+        verts.append(v[used] + rng.normal(0, 3.0, 3))
+        tets.append(remap[keep])
+    off = np.cumsum([0] + [len(v) for v in verts])
+    V = np.concatenate(verts)
+    T = np.concatenate([t + off[i] for i, t in enumerate(tets)])
+    n_total = len(V) + int(rng.integers(0, 6))                                  # extra unreferenced vertices
+    perm = rng.permutation(n_total)
+    Vp = rng.normal(0, 1, (n_total, 3))
+    Vp[perm[: len(V)]] = V
+    Tp = perm[T]
+    Tp = Tp[rng.permutation(len(Tp))]
+    return Vp.astype(np.float32), Tp.astype(np.int32)
+
+
+def test_plan_randomised_ragged_meshes_match_oracle():
+    """Property test of the host plan builder + stream format: for random ragged, relabelled, interleaved
+    multi-component meshes and random launch shapes, the numpy walk of the plan equals the fp64 C oracle."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(seed=st.integers(0, 10 ** 6), n_comp=st.integers(1, 5), nw=st.sampled_from([8, 16]), grid=st.integers(1, 9),
+           force_global=st.sampled_from([0, 1]), scale=st.sampled_from([0, 1]))
+    def run(seed, n_comp, nw, grid, force_global, scale):
+        rng = np.random.default_rng(seed)
+        V, T = _ragged_mesh(rng, n_comp, 400)
+        if len(np.unique(T)) < 4:
+            return
+        plan = build_host_plan(V, T, nw=nw, grid=grid, force_global=force_global, laplacian_scale=scale)
+        orc = COracle(V, T, scale)
+        for sig, order in ((0.03, 2), (0.4, 4)):
+            x = (V + rng.normal(0, sig * 0.2, V.shape)).astype(np.float32)
+            E, es, eb, g = emulate_kernel(plan, x, 3e-4, 2e-4, order, gradH=1.3)
+            Eo, terms, go = orc.energy_grad(x, 3e-4, 2e-4, order, gradH=1.3)
+            assert E == pytest.approx(Eo, rel=5e-6, abs=1e-12)
+            assert np.linalg.norm(g - go) <= 5e-6 * max(np.linalg.norm(go), 1e-12)
+    run()
