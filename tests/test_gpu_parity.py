@@ -577,3 +577,21 @@ def test_native_autograd_bridge_matches_python_function(ext):
         assert np.linalg.norm(x.grad.cpu().numpy() - go) <= REL * np.linalg.norm(go)
     finally:
         energies.use_native_autograd = True
+
+
+def test_randomised_ragged_meshes_on_gpu(ext):
+    """The kernel on random ragged, relabelled, interleaved multi-component meshes (unreferenced vertices, components
+    of very different sizes) in every variant, against the fp64 C oracle."""
+    from test_host_logic import _ragged_mesh
+    for seed in range(8):
+        rng = np.random.default_rng(100 + seed)
+        V, T = _ragged_mesh(rng, int(rng.integers(1, 7)), 1200)
+        orc = COracle(V, T)
+        for kw in ({}, {"warps_per_cta": 8}, {"force_global": True}):
+            sp = ext.TetSpheres(V.reshape(-1), T.reshape(-1), **kw)
+            for sig, order in ((0.03, 2), (0.4, 4)):
+                x_np = (V + rng.normal(0, sig * 0.2, V.shape)).astype(np.float32)
+                e, g = sp.energy_grad(torch.from_numpy(x_np).cuda(), 3e-4, 2e-4, order, 1.3)
+                eo, _, go = orc.energy_grad(x_np, 3e-4, 2e-4, order, gradH=1.3)
+                assert float(e[0]) == pytest.approx(eo, rel=REL, abs=1e-12), (seed, kw, sig)
+                assert np.linalg.norm(g.cpu().numpy() - go) <= REL * max(np.linalg.norm(go), 1e-12), (seed, kw, sig)
