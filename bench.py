@@ -603,7 +603,20 @@ def main():
                 # launch on the same sphere
                 one = packs[0].slice_spheres(0, 1)
                 v0 = int(packs[0].vert_offsets[1])
-                t1s, _, _ = time_fwd_bwd(one.verts, one.tets, x0[:v0], c1, c2, ORDER, iters=10, warmup=2, threads=best[1])
+                t1s, _, _ = time_fwd_bwd(one.verts, one.tets, x0[:v0], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
+                s16 = packs[0].slice_spheres(0, 16)
+                v16 = int(packs[0].vert_offsets[16])
+                t16s, _, _ = time_fwd_bwd(s16.verts, s16.tets, x0[:v16], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
+                cpu_model = ""
+                try:
+                    with open("/proc/cpuinfo") as f:
+                        cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+                except OSError:
+                    pass
+                out["extras"]["host"] = {"cpu_model": cpu_model, "os_cpu_count": os.cpu_count(), "threads_available": avail}
+                if "config1_16_spheres" in out["extras"]:
+                    out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_ms_per_fwd_bwd"] = t16s * 1e3
+                    out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_threads"] = best[1]
                 out["extras"]["config0_1_sphere"] = {
                     "vanilla_torch_cpu_ms_per_fwd_bwd": t1s * 1e3, "threads": best[1],
                     "b200_fused_launch_us": extras_1sphere_us,
