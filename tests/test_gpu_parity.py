@@ -595,3 +595,19 @@ def test_randomised_ragged_meshes_on_gpu(ext):
                 eo, _, go = orc.energy_grad(x_np, 3e-4, 2e-4, order, gradH=1.3)
                 assert float(e[0]) == pytest.approx(eo, rel=REL, abs=1e-12), (seed, kw, sig)
                 assert np.linalg.norm(g.cpu().numpy() - go) <= REL * max(np.linalg.norm(go), 1e-12), (seed, kw, sig)
+
+
+def test_thousands_of_tiny_components(ext):
+    """2600 twelve-tet components: more segments per CTA (18) than the shared-memory segment table holds (16), many
+    staging hand-overs per CTA, every variant."""
+    pk = make_pack(2600, 12, seed=3, unique=6)
+    orc = COracle(pk.verts, pk.tets)
+    rng = np.random.default_rng(0)
+    for kw in ({}, {"warps_per_cta": 8}, {"force_global": True}):
+        sp = ext.TetSpheres(pk.verts.reshape(-1), pk.tets.reshape(-1), **kw)
+        for sig, order in ((0.02, 2), (0.3, 4)):
+            x_np = (pk.verts + rng.normal(0, sig, pk.verts.shape)).astype(np.float32)
+            e, g = sp.energy_grad(torch.from_numpy(x_np).cuda(), 2e-4, 3e-4, order)
+            eo, _, go = orc.energy_grad(x_np, 2e-4, 3e-4, order)
+            assert float(e[0]) == pytest.approx(eo, rel=REL), (kw, sig)
+            assert np.linalg.norm(g.cpu().numpy() - go) <= REL * np.linalg.norm(go), (kw, sig)

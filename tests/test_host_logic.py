@@ -336,3 +336,16 @@ def test_plan_randomised_ragged_meshes_match_oracle():
             assert E == pytest.approx(Eo, rel=5e-6, abs=1e-12)
             assert np.linalg.norm(g - go) <= 5e-6 * max(np.linalg.norm(go), 1e-12)
     run()
+
+
+def test_plan_thousands_of_tiny_components():
+    """2600 twelve-tet components on 148 CTAs: up to 18 segments per CTA (more than the kernel's 16-entry
+    shared-memory segment table, so the global fallback path of the headers is part of the plan's contract)."""
+    pk = make_pack(2600, 12, seed=3, unique=6)
+    plan = build_host_plan(pk.verts, pk.tets, nw=16, grid=148)
+    cs = plan["cta_seg"].reshape(-1, 2)
+    assert plan["n_components"] == 2600 and (cs[:, 1] - cs[:, 0]).max() > 16
+    x = (pk.verts + np.random.default_rng(0).normal(0, 0.05, pk.verts.shape)).astype(np.float32)
+    E, _, _, g = emulate_kernel(plan, x, 2e-4, 3e-4, 2)
+    Eo, _, go = COracle(pk.verts, pk.tets).energy_grad(x, 2e-4, 3e-4, 2)
+    assert E == pytest.approx(Eo, rel=2e-6) and np.linalg.norm(g - go) <= 2e-6 * np.linalg.norm(go)
