@@ -583,12 +583,17 @@ def main():
             # the CPU port, timed in a child process (pinned OpenMP threads, all host cores): `--impl reference` itself
             import subprocess
             env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS",)}
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--min-seconds", "10"],
-                               capture_output=True, text=True, env=env, timeout=600)
             try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--min-seconds", "10"],
+                                   capture_output=True, text=True, env=env, timeout=600)
                 out["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
-            except Exception:
-                raise RuntimeError("cpu_baseline leg failed: " + r.stderr[-2000:])
+            except Exception as ex:      # keep the GPU line: time the port in this process instead (threads not pinned)
+                dt0, variant, cores, co = _calibrate(packs[0], x0, c1, c2)
+                ts = _time_cpu(co, x0, c1, c2, cores, min_seconds=10.0, min_steps=200)
+                out["cpu_baseline"] = {"value": 1.0 / float(np.median(ts)), "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": f"{len(ts)} energy+gradient iterations of the full 64-sphere pack, median step; "
+                                                 f"matrix-free C port, {_variant_name(variant)}, OpenMP {cores} threads, NOT pinned "
+                                                 f"(the pinned child process failed: {type(ex).__name__})"}
             if not args.no_extras:
                 # the reference-shaped "vanilla PyTorch" pipeline (SpMV GTLTLG, SpMV G, autograd), best thread count
                 from oracle.torch_energy import time_fwd_bwd
