@@ -504,18 +504,21 @@ def main():
 
     if not args.no_extras and not strong and n_sph == SPHERES:
         if world == 1:
-            sec1, _, _ = one_pack_rate(1, 7000)
-            extras_1sphere_us = sec1 * 1e6
-            sec, b16, _ = one_pack_rate(16, 7001)
-            extras["config1_16_spheres"] = {"us_per_step": sec * 1e6, "iters_per_s": 1.0 / sec, "hbm_frac_by_B_alg": b16 / sec / 1e9 / peak,
-                                            "note": "BASELINE configs[1]: 16 tet-spheres, fused kernel only, fp32, 1 GPU (L2-resident)"}
-            sec, b1k, inf = one_pack_rate(1024, 7002)
-            extras["config4_1024_spheres_one_gpu"] = {"us_per_step": sec * 1e6, "algorithmic_GBps": b1k / sec / 1e9,
-                                                      "hbm_frac_by_B_alg": b1k / sec / 1e9 / peak,
-                                                      "plan_stream_GBps": inf["stream_bytes"] / sec / 1e9,
-                                                      "tsb_create_seconds": create_s.get(1024),
-                                                      "note": "BASELINE configs[4] pack (1024 spheres, 4.2 M tets) on ONE GPU: "
-                                                              "306 MB of plan data per step, HBM-streaming regime"}
+            try:      # single process: an extra that fails is reported, the headline line still prints
+                sec1, _, _ = one_pack_rate(1, 7000)
+                extras_1sphere_us = sec1 * 1e6
+                sec, b16, _ = one_pack_rate(16, 7001)
+                extras["config1_16_spheres"] = {"us_per_step": sec * 1e6, "iters_per_s": 1.0 / sec, "hbm_frac_by_B_alg": b16 / sec / 1e9 / peak,
+                                                "note": "BASELINE configs[1]: 16 tet-spheres, fused kernel only, fp32, 1 GPU (L2-resident)"}
+                sec, b1k, inf = one_pack_rate(1024, 7002)
+                extras["config4_1024_spheres_one_gpu"] = {"us_per_step": sec * 1e6, "algorithmic_GBps": b1k / sec / 1e9,
+                                                          "hbm_frac_by_B_alg": b1k / sec / 1e9 / peak,
+                                                          "plan_stream_GBps": inf["stream_bytes"] / sec / 1e9,
+                                                          "tsb_create_seconds": create_s.get(1024),
+                                                          "note": "BASELINE configs[4] pack (1024 spheres, 4.2 M tets) on ONE GPU: "
+                                                                  "306 MB of plan data per step, HBM-streaming regime"}
+            except Exception as ex:  # pragma: no cover
+                extras["size_sweep_error"] = repr(ex)
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 from energy_only_loop import run as loop_run
@@ -595,42 +598,45 @@ def main():
                                                  f"matrix-free C port, {_variant_name(variant)}, OpenMP {cores} threads, NOT pinned "
                                                  f"(the pinned child process failed: {type(ex).__name__})"}
             if not args.no_extras:
-                # the reference-shaped "vanilla PyTorch" pipeline (SpMV GTLTLG, SpMV G, autograd), best thread count
-                from oracle.torch_energy import time_fwd_bwd
-                best, ns, avail = None, 2, _host_threads()
-                sub = packs[0].slice_spheres(0, ns)
-                v1 = int(packs[0].vert_offsets[ns])
-                for th in sorted({min(avail, 8), min(avail, 32), avail}):
-                    tt_, _, _ = time_fwd_bwd(sub.verts, sub.tets, x0[:v1], c1, c2, ORDER, iters=4, warmup=1, threads=th)
-                    if best is None or tt_ < best[0]:
-                        best = (tt_, th)
-                # BASELINE configs[0]: ONE tet-sphere, vanilla-PyTorch forward+backward on the host cores, beside the fused
-                # launch on the same sphere
-                one = packs[0].slice_spheres(0, 1)
-                v0 = int(packs[0].vert_offsets[1])
-                t1s, _, _ = time_fwd_bwd(one.verts, one.tets, x0[:v0], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
-                s16 = packs[0].slice_spheres(0, 16)
-                v16 = int(packs[0].vert_offsets[16])
-                t16s, _, _ = time_fwd_bwd(s16.verts, s16.tets, x0[:v16], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
-                cpu_model = ""
                 try:
-                    with open("/proc/cpuinfo") as f:
-                        cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
-                except OSError:
-                    pass
-                out["extras"]["host"] = {"cpu_model": cpu_model, "os_cpu_count": os.cpu_count(), "threads_available": avail}
-                if "config1_16_spheres" in out["extras"]:
-                    out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_ms_per_fwd_bwd"] = t16s * 1e3
-                    out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_threads"] = best[1]
-                out["extras"]["config0_1_sphere"] = {
-                    "vanilla_torch_cpu_ms_per_fwd_bwd": t1s * 1e3, "threads": best[1],
-                    "b200_fused_launch_us": extras_1sphere_us,
-                    "note": "BASELINE configs[0]: 1 tet-sphere x 4096 tets; torch sparse fp32 + autograd restatement of the "
-                            "reference's SpMV pipeline on the CPU vs ONE fused energy+grad launch (graph replay)"}
-                out["extras"]["cpu_torch_restatement_iters_per_s"] = 1.0 / (best[0] * SPHERES / ns)
-                out["extras"]["cpu_torch_restatement_note"] = (f"torch sparse fp32 + autograd restatement of the reference's SpMV "
-                                                               f"pipeline, {ns} of {SPHERES} spheres extrapolated, best of thread "
-                                                               f"counts -> {best[1]} threads")
+                    # the reference-shaped "vanilla PyTorch" pipeline (SpMV GTLTLG, SpMV G, autograd), best thread count
+                    from oracle.torch_energy import time_fwd_bwd
+                    best, ns, avail = None, 2, _host_threads()
+                    sub = packs[0].slice_spheres(0, ns)
+                    v1 = int(packs[0].vert_offsets[ns])
+                    for th in sorted({min(avail, 8), min(avail, 32), avail}):
+                        tt_, _, _ = time_fwd_bwd(sub.verts, sub.tets, x0[:v1], c1, c2, ORDER, iters=4, warmup=1, threads=th)
+                        if best is None or tt_ < best[0]:
+                            best = (tt_, th)
+                    # BASELINE configs[0]: ONE tet-sphere, vanilla-PyTorch forward+backward on the host cores, beside the fused
+                    # launch on the same sphere
+                    one = packs[0].slice_spheres(0, 1)
+                    v0 = int(packs[0].vert_offsets[1])
+                    t1s, _, _ = time_fwd_bwd(one.verts, one.tets, x0[:v0], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
+                    s16 = packs[0].slice_spheres(0, 16)
+                    v16 = int(packs[0].vert_offsets[16])
+                    t16s, _, _ = time_fwd_bwd(s16.verts, s16.tets, x0[:v16], c1, c2, ORDER, iters=20, warmup=3, threads=best[1])
+                    cpu_model = ""
+                    try:
+                        with open("/proc/cpuinfo") as f:
+                            cpu_model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "")
+                    except OSError:
+                        pass
+                    out["extras"]["host"] = {"cpu_model": cpu_model, "os_cpu_count": os.cpu_count(), "threads_available": avail}
+                    if "config1_16_spheres" in out["extras"]:
+                        out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_ms_per_fwd_bwd"] = t16s * 1e3
+                        out["extras"]["config1_16_spheres"]["vanilla_torch_cpu_threads"] = best[1]
+                    out["extras"]["config0_1_sphere"] = {
+                        "vanilla_torch_cpu_ms_per_fwd_bwd": t1s * 1e3, "threads": best[1],
+                        "b200_fused_launch_us": extras_1sphere_us,
+                        "note": "BASELINE configs[0]: 1 tet-sphere x 4096 tets; torch sparse fp32 + autograd restatement of the "
+                                "reference's SpMV pipeline on the CPU vs ONE fused energy+grad launch (graph replay)"}
+                    out["extras"]["cpu_torch_restatement_iters_per_s"] = 1.0 / (best[0] * SPHERES / ns)
+                    out["extras"]["cpu_torch_restatement_note"] = (f"torch sparse fp32 + autograd restatement of the reference's SpMV "
+                                                                   f"pipeline, {ns} of {SPHERES} spheres extrapolated, best of thread "
+                                                                   f"counts -> {best[1]} threads")
+                except Exception as ex:      # extras never cost the headline line
+                    out["extras"]["cpu_torch_restatement_error"] = f"{type(ex).__name__}: {ex}"
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
